@@ -1,0 +1,188 @@
+"""GPU parity tests: the CUDA path (through the reference-signature Python API, which calls the
+C ABI) against the CPU oracle and against the committed outputs of the reference's own source.
+
+Tolerances: fp64 mode 1e-10 relative on energy and gradient (north star); mixed mode 1e-5.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import uind_dense  # noqa: E402  (checker only)
+from u_pol_b200 import polarization as pol  # noqa: E402
+from u_pol_b200 import synth, util  # noqa: E402
+from u_pol_b200.engine import UindSystem  # noqa: E402
+from u_pol_b200.topology import DrudeSystem  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL_FP64 = 1e-10
+RTOL_MIXED = 1e-5
+
+
+def _load(npz, name):
+    return DrudeSystem(r_core=npz[f"{name}/r_core"], q_core=npz[f"{name}/q_core"], q_shell=npz[f"{name}/q_shell"],
+                       alpha=npz[f"{name}/alpha"], thole_u=npz[f"{name}/thole_u"], site_names=[])
+
+
+def _dense(s):
+    Rij, _ = util.get_Rij_Dij(s)
+    Qi_core, Qi_shell, Qj_core, Qj_shell = util.get_QiQj(s)
+    k, u_scale = util.get_pol_params(s)
+    return Rij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k
+
+
+def _sum_abs_terms(s):
+    """K * sum over inter-molecular site pairs of |q_i||q_j|/R with |q| = |qc| + |qs|."""
+    r = s.r_core.reshape(-1, 3)
+    q = (np.abs(s.q_core) + np.abs(s.q_shell)).reshape(-1)
+    mol = np.repeat(np.arange(s.nmol), s.natoms)
+    R = np.linalg.norm(r[:, None, :] - r[None, :, :], axis=-1)
+    mask = mol[:, None] != mol[None, :]
+    with np.errstate(divide="ignore"):
+        t = np.where(mask & (R > 0), q[:, None] * q[None, :] / np.where(R > 0, R, 1.0), 0.0)
+    return 0.5 * 138.93545764438198 * t.sum()
+
+
+REF_SYSTEMS = ["water", "acnit", "imidazole_trimer", "imidazole_dimer10", "imidazole3", "water_box27", "imidazole_box12"]
+DSETS = ["zero", "pattern", "random", "random_all_sites"]
+
+
+@pytest.fixture(scope="module")
+def ref_exec():
+    return np.load(os.path.join(GOLD, "ref_exec.npz"))
+
+
+def test_constant(ref_exec):
+    assert pol.set_constants() == float(ref_exec["ONE_4PI_EPS0"]) == 138.93545764438198
+
+
+@pytest.mark.parametrize("name", REF_SYSTEMS)
+@pytest.mark.parametrize("dset", DSETS)
+def test_uind_and_grad_vs_reference_source(ref_exec, name, dset):
+    """Energies/gradients recorded from the reference's own Uind + reverse-mode AD."""
+    s = _load(ref_exec, name)
+    Rij, Qis, Qjs, Qic, Qjc, u, k = _dense(s)
+    D = ref_exec[f"{name}/{dset}/D"]
+    e, g = pol.Uind_and_grad(Rij, D, Qis, Qjs, Qic, Qjc, u, k)
+    e_ref, g_ref = float(ref_exec[f"{name}/{dset}/Uind"]), ref_exec[f"{name}/{dset}/grad"]
+    # U_ind is the difference U_coul - U_static of sums whose terms are far larger than the result
+    # (at d=0 it is pure round-off, ~1e-13, in the reference itself): fp64 epsilon times the sum
+    # of absolute pair terms is the floor below which "relative to U_ind" has no meaning.
+    assert abs(float(e) - e_ref) <= RTOL_FP64 * abs(e_ref) + 1e-14 * _sum_abs_terms(s)
+    assert np.abs(g.cpu().numpy() - g_ref).max() <= RTOL_FP64 * np.abs(g_ref).max()
+    # rows without a Drude: exactly zero
+    assert np.all(g.cpu().numpy()[s.q_shell == 0] == 0.0)
+
+
+@pytest.mark.parametrize("name", REF_SYSTEMS)
+def test_components_vs_reference_source(ref_exec, name):
+    s = _load(ref_exec, name)
+    Rij, Qis, Qjs, Qic, Qjc, u, k = _dense(s)
+    D = ref_exec[f"{name}/random/D"]
+    ucs = float(pol.Ucoul_static(Rij, Qis, Qjs, Qic, Qjc))
+    ref_ucs = float(ref_exec[f"{name}/Ucoul_static"])
+    assert abs(ucs - ref_ucs) <= RTOL_FP64 * abs(ref_ucs)
+    uc = float(pol.Ucoul(Rij, D, Qis, Qjs, Qic, Qjc, u))
+    ref_uc = float(ref_exec[f"{name}/random/Ucoul"])
+    assert abs(uc - ref_uc) <= RTOL_FP64 * abs(ref_uc)
+    us = float(pol.Uself(D, k))
+    assert abs(us - float(ref_exec[f"{name}/random/Uself"])) <= RTOL_FP64 * abs(us)
+    if f"{name}/make_Sij" in ref_exec:
+        S = pol.make_Sij(Rij, u).cpu().numpy()
+        assert np.abs(S - ref_exec[f"{name}/make_Sij"]).max() <= 1e-14
+
+
+def test_flat_dij_and_torch_inputs(ref_exec):
+    s = _load(ref_exec, "acnit")
+    Rij, Qis, Qjs, Qic, Qjc, u, k = _dense(s)
+    D = ref_exec["acnit/random/D"]
+    e1 = float(pol.Uind(Rij, D, Qis, Qjs, Qic, Qjc, u, k))
+    e2 = float(pol.Uind(torch.as_tensor(Rij), torch.as_tensor(D.ravel()), torch.as_tensor(Qis), torch.as_tensor(Qjs),
+                        torch.as_tensor(Qic), torch.as_tensor(Qjc), torch.as_tensor(u), torch.as_tensor(k)))
+    assert e1 == e2
+
+
+@pytest.mark.parametrize("maker,nmol,seed", [(synth.water_box, 64, 21), (synth.water_box, 343, 22),
+                                             (synth.imidazole_box, 27, 23), (synth.imidazole_box, 125, 24)])
+def test_random_boxes_vs_oracle(maker, nmol, seed):
+    s = maker(nmol, seed=seed)
+    Rij, Qis, Qjs, Qic, Qjc, u, k = _dense(s)
+    D = synth.random_displacements(s, seed=seed + 100)
+    e_ref, g_ref = uind_dense.u_ind_and_grad(Rij, D, Qis, Qjs, Qic, Qjc, u, k)
+    sys_ = UindSystem.from_drude_system(s)
+    e, g = sys_.energy_grad(D)
+    assert abs(float(e[0]) - e_ref) <= RTOL_FP64 * abs(e_ref) + 1e-14 * _sum_abs_terms(s)
+    assert np.abs(g.cpu().numpy().reshape(g_ref.shape) - g_ref).max() <= RTOL_FP64 * np.abs(g_ref).max()
+    # host-buffer entry point gives the same numbers
+    eh, gh = sys_.energy_grad_host(D)
+    assert eh[0] == float(e[0]) and np.array_equal(gh, g.cpu().numpy())
+    # mixed precision: fp32 field, fp64 potential
+    em, gm = sys_.energy_grad(D, precision="mixed")
+    assert abs(float(em[0]) - e_ref) <= RTOL_MIXED * abs(e_ref)
+    assert np.abs(gm.cpu().numpy().reshape(g_ref.shape) - g_ref).max() <= RTOL_MIXED * np.abs(g_ref).max()
+    assert np.linalg.norm(gm.cpu().numpy().reshape(g_ref.shape) - g_ref) <= RTOL_MIXED * np.linalg.norm(g_ref)
+
+
+def test_zero_distance_and_padding_sites():
+    """Zero-distance terms are dropped (polarization.py:33-42): zero-charge padding sites placed
+    on top of real sites of ANOTHER molecule change nothing."""
+    s = synth.water_box(8, seed=5)
+    r = s.r_core.copy()
+    qc, qs, al = s.q_core.copy(), s.q_shell.copy(), s.alpha.copy()
+    # append a padding site to every molecule, coincident with the O of the next molecule
+    pad = np.roll(r[:, 0, :], -1, axis=0)[:, None, :]
+    r2 = np.concatenate([r, pad], axis=1)
+    z = np.zeros((s.nmol, 1))
+    s2 = DrudeSystem(r_core=r2, q_core=np.concatenate([qc, z], 1), q_shell=np.concatenate([qs, z], 1),
+                     alpha=np.concatenate([al, z], 1), thole_u=np.zeros((s.nmol, 5, 5)), site_names=[])
+    D = synth.random_displacements(s, seed=9)
+    D2 = np.concatenate([D, np.zeros((s.nmol, 1, 3))], axis=1)
+    e1, g1 = UindSystem.from_drude_system(s).energy_grad(D)
+    e2, g2 = UindSystem.from_drude_system(s2).energy_grad(D2)
+    assert abs(float(e1[0]) - float(e2[0])) <= 1e-12 * abs(float(e1[0]))
+    g2 = g2.cpu().numpy().reshape(s.nmol, 5, 3)
+    assert np.abs(g2[:, :4] - g1.cpu().numpy().reshape(s.nmol, 4, 3)).max() <= 1e-12 * np.abs(g2).max()
+    Rij, Qis, Qjs, Qic, Qjc, u, k = _dense(s2)
+    e_ref, _ = uind_dense.u_ind_and_grad(Rij, D2, Qis, Qjs, Qic, Qjc, u, k)
+    assert abs(float(e2[0]) - e_ref) <= RTOL_FP64 * abs(e_ref) + 1e-14 * _sum_abs_terms(s2)
+
+
+def test_gradient_finite_difference():
+    s = synth.imidazole_box(8, seed=31)
+    sys_ = UindSystem.from_drude_system(s)
+    D = synth.random_displacements(s, seed=32)
+    _, g = sys_.energy_grad(D)
+    g = g.cpu().numpy().reshape(D.shape)
+    rng = np.random.default_rng(0)
+    pol_sites = np.argwhere(s.q_shell != 0)
+    for m, a in pol_sites[rng.choice(len(pol_sites), 6, replace=False)]:
+        for c in range(3):
+            h = 1e-6
+            Dp, Dm = D.copy(), D.copy()
+            Dp[m, a, c] += h
+            Dm[m, a, c] -= h
+            fd = (float(sys_.energy_grad(Dp, want_grad=False)[0][0]) - float(sys_.energy_grad(Dm, want_grad=False)[0][0])) / (2 * h)
+            assert abs(fd - g[m, a, c]) <= 1e-6 * max(1.0, abs(g[m, a, c]))
+
+
+def test_row_shard_slices_sum_to_whole():
+    """Multi-GPU emulation on one device: the row shards of 3 'ranks' add up to the full result."""
+    s = synth.imidazole_box(30, seed=41)
+    D = synth.random_displacements(s, seed=42)
+    full = UindSystem.from_drude_system(s)
+    e, g = full.energy_grad(D)
+    e_sum, g_sum = torch.zeros_like(e), torch.zeros_like(g)
+    from u_pol_b200.engine import shard_bounds
+    for rank in range(3):
+        part = UindSystem.from_drude_system(s)
+        part.set_row_range(*shard_bounds(s.nmol, 3, rank))
+        ep, gp = part.energy_grad(D)
+        lo, hi = shard_bounds(s.nmol, 3, rank)
+        g_sum[lo * s.natoms: hi * s.natoms] += gp[lo * s.natoms: hi * s.natoms]
+        e_sum[1:6] += ep[1:6]
+    u = float((e_sum[1] + e_sum[5] + e_sum[2]) + e_sum[3])
+    assert abs(u - float(e[0])) <= 1e-12 * abs(float(e[0]))
+    assert torch.allclose(g_sum, g, rtol=0, atol=1e-12 * float(g.abs().max()))

@@ -1,0 +1,393 @@
+// extern "C" entry points of libupol_b200.so (see include/upol_b200.h for the contract and the
+// reference lines each one replaces).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+using namespace upol;
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int dev_alloc(T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return UPOL_ERR_ALLOC; }
+    return UPOL_OK;
+}
+
+template <typename T>
+int upload(T *dst, const std::vector<T> &src) {
+    if (src.empty()) return UPOL_OK;
+    UPOL_CUDA(cudaMemcpy(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return UPOL_OK;
+}
+
+void free_system(upol_system *s) {
+    if (!s) return;
+    minimize_free(s);
+    comm_destroy(s);
+    void *ptrs[] = {s->r, s->qc, s->qs, s->k, s->row_site, s->row_qs, s->row_k, s->exA_lo, s->exA_len,
+                    s->exB_lo, s->exB_len, s->rowx, s->rowy, s->rowz, s->srowx, s->srowy, s->srowz,
+                    s->cols, s->cols_f, s->cols_static, s->th_ptr, s->th_row, s->th_u, s->part, s->dc,
+                    s->gc, s->eblock, s->energy, s->e_static};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (s->pin) cudaFreeHost(s->pin);
+    delete s;
+}
+
+void compute_centre(upol_system *s, const double *r_host) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t i = 0; i < s->nsite; ++i)
+        for (int c = 0; c < 3; ++c) {
+            lo[c] = std::min(lo[c], r_host[3 * i + c]);
+            hi[c] = std::max(hi[c], r_host[3 * i + c]);
+        }
+    for (int c = 0; c < 3; ++c) s->centre[c] = s->nsite ? 0.5 * (lo[c] + hi[c]) : 0.0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *upol_error_string(int code) {
+    switch (code) {
+        case UPOL_OK: return "ok";
+        case UPOL_ERR_CUDA: return last_error_message();
+        case UPOL_ERR_ARG: return "invalid argument";
+        case UPOL_ERR_NCCL: return "NCCL error or NCCL library not available";
+        case UPOL_ERR_ALLOC: return last_error_message();
+        default: return code > 0 ? "numerical flag (see UPOL_FLAG_*)" : "unknown error";
+    }
+}
+
+int upol_version(void) { return 100; }
+
+double upol_one_4pi_eps0(void) { return kCoulomb; }
+
+int upol_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int upol_system_create(upol_system **out, int device, int64_t nsite, const double *r_core,
+                       const double *q_core, const double *q_shell, const double *k,
+                       const int32_t *mol_id, int64_t npair, const int32_t *pair_a,
+                       const int32_t *pair_b, const double *pair_u) {
+    if (!out || nsite <= 0 || !r_core || !q_core || !q_shell || !k || !mol_id || npair < 0) return UPOL_ERR_ARG;
+    if (nsite > (int64_t)1 << 30) return UPOL_ERR_ARG;
+    *out = nullptr;
+    DeviceGuard guard(device);
+    if (!guard.ok) { set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__); return UPOL_ERR_CUDA; }
+
+    upol_system *s = new (std::nothrow) upol_system();
+    if (!s) return UPOL_ERR_ALLOC;
+    s->device = device;
+    s->nsite = nsite;
+    s->h_mol.assign(mol_id, mol_id + nsite);
+    s->h_qc.assign(q_core, q_core + nsite);
+    s->h_qs.assign(q_shell, q_shell + nsite);
+    s->h_k.assign(k, k + nsite);
+
+    // molecules: contiguous runs of equal mol_id
+    s->h_site_row.assign(nsite, -1);
+    std::vector<int32_t> site_mol(nsite);
+    for (int64_t i = 0; i < nsite; ++i) {
+        if (i > 0 && mol_id[i] < mol_id[i - 1]) { delete s; return UPOL_ERR_ARG; }
+        if (i == 0 || mol_id[i] != mol_id[i - 1]) {
+            s->h_mol_site0.push_back((int32_t)i);
+            s->h_mol_nsite.push_back(0);
+            s->h_mol_row0.push_back((int32_t)s->h_drude_site.size());
+            s->h_mol_nrow.push_back(0);
+        }
+        const int m = (int)s->h_mol_site0.size() - 1;
+        site_mol[i] = m;
+        s->h_mol_nsite[m]++;
+        if (q_shell[i] != 0.0) {
+            s->h_site_row[i] = (int32_t)s->h_drude_site.size();
+            s->h_drude_site.push_back((int32_t)i);
+            s->h_mol_nrow[m]++;
+        }
+    }
+    s->h_mol = site_mol;   // dense molecule index from here on
+    s->nmol = (int64_t)s->h_mol_site0.size();
+    s->nd = (int64_t)s->h_drude_site.size();
+    s->nd_pad = round_up(std::max<int64_t>(s->nd, 1), 512);
+    s->na_pad = round_up(nsite, kTileCols);
+    s->nb_pad = round_up(std::max<int64_t>(s->nd, 1), kTileCols);
+    s->mol_lo = 0; s->mol_hi = s->nmol; s->row_lo = 0; s->row_hi = s->nd;
+
+    // per-row tables
+    std::vector<int32_t> exA_lo(s->nd_pad, 0), exA_len(s->nd_pad, 0), exB_lo(s->nd_pad, 0), exB_len(s->nd_pad, 0);
+    std::vector<double> row_qs(std::max<int64_t>(s->nd, 1), 0.0), row_k(std::max<int64_t>(s->nd, 1), 0.0);
+    for (int64_t i = 0; i < s->nd; ++i) {
+        const int site = s->h_drude_site[i];
+        const int m = site_mol[site];
+        exA_lo[i] = s->h_mol_site0[m];
+        exA_len[i] = s->h_mol_nsite[m];
+        exB_lo[i] = (int32_t)s->na_pad + s->h_mol_row0[m];   // concatenated column index
+        exB_len[i] = s->h_mol_nrow[m];
+        row_qs[i] = q_shell[site];
+        row_k[i] = k[site];
+    }
+    // screened pairs -> CSR of ordered pairs over Drude rows
+    std::vector<int32_t> th_ptr(s->nd + 1, 0), th_row;
+    std::vector<double> th_u;
+    {
+        std::vector<std::vector<std::pair<int32_t, double>>> adj(s->nd);
+        for (int64_t p = 0; p < npair; ++p) {
+            const int a = pair_a[p], b = pair_b[p];
+            if (a < 0 || b < 0 || a >= nsite || b >= nsite || a == b || site_mol[a] != site_mol[b]) { delete s; return UPOL_ERR_ARG; }
+            const int ra = s->h_site_row[a], rb = s->h_site_row[b];
+            if (ra < 0 || rb < 0 || pair_u[p] == 0.0) continue;   // S == 0 for a non-polarisable partner / u = 0
+            adj[ra].push_back({rb, pair_u[p]});
+            adj[rb].push_back({ra, pair_u[p]});
+        }
+        for (int64_t i = 0; i < s->nd; ++i) {
+            std::sort(adj[i].begin(), adj[i].end());
+            for (auto &e : adj[i]) { th_row.push_back(e.first); th_u.push_back(e.second); }
+            th_ptr[i + 1] = (int32_t)th_row.size();
+        }
+    }
+    s->npair_ordered = (int64_t)th_row.size();
+
+    // Column splits S are chosen per launch so that (row blocks * S) ~ 148*8 (choose_split);
+    // with rb row blocks of <= 512 rows, S*stride <= (1184/rb + 1)(512 rb + 511), which the
+    // allocation below covers for the full system and for every row shard of it.
+    s->max_split = 256;
+    const size_t part_elems = (size_t)kPartComps * ((size_t)148 * 8 * 1024 + (size_t)s->nd_pad + 1024);
+
+    int rc = UPOL_OK;
+#define TRY(x) do { rc = (x); if (rc) { free_system(s); return rc; } } while (0)
+    TRY(dev_alloc(&s->r, 3 * nsite));
+    TRY(dev_alloc(&s->qc, nsite)); TRY(dev_alloc(&s->qs, nsite)); TRY(dev_alloc(&s->k, nsite));
+    TRY(dev_alloc(&s->row_site, s->nd)); TRY(dev_alloc(&s->row_qs, s->nd)); TRY(dev_alloc(&s->row_k, s->nd));
+    TRY(dev_alloc(&s->exA_lo, s->nd_pad)); TRY(dev_alloc(&s->exA_len, s->nd_pad));
+    TRY(dev_alloc(&s->exB_lo, s->nd_pad)); TRY(dev_alloc(&s->exB_len, s->nd_pad));
+    TRY(dev_alloc(&s->rowx, s->nd_pad)); TRY(dev_alloc(&s->rowy, s->nd_pad)); TRY(dev_alloc(&s->rowz, s->nd_pad));
+    TRY(dev_alloc(&s->srowx, s->nd_pad)); TRY(dev_alloc(&s->srowy, s->nd_pad)); TRY(dev_alloc(&s->srowz, s->nd_pad));
+    TRY(dev_alloc(&s->cols, s->na_pad + s->nb_pad));
+    TRY(dev_alloc(&s->cols_f, s->na_pad + s->nb_pad));
+    TRY(dev_alloc(&s->cols_static, s->na_pad));
+    TRY(dev_alloc(&s->th_ptr, s->nd + 1)); TRY(dev_alloc(&s->th_row, th_row.size())); TRY(dev_alloc(&s->th_u, th_u.size()));
+    TRY(dev_alloc(&s->part, part_elems));
+    TRY(dev_alloc(&s->dc, 3 * s->nd)); TRY(dev_alloc(&s->gc, 3 * s->nd));
+    s->n_eblock = (int)((std::max<int64_t>(s->nd, nsite) + 127) / 128) + 1;
+    TRY(dev_alloc(&s->eblock, 4 * (size_t)s->n_eblock));
+    TRY(dev_alloc(&s->energy, UPOL_E_SIZE)); TRY(dev_alloc(&s->e_static, 2));
+
+    {
+        cudaError_t e = cudaSuccess;
+        auto cp = [&](void *dst, const void *src, size_t bytes) {
+            if (e == cudaSuccess && bytes) e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+        };
+        cp(s->r, r_core, sizeof(double) * 3 * nsite);
+        cp(s->qc, q_core, sizeof(double) * nsite);
+        cp(s->qs, q_shell, sizeof(double) * nsite);
+        cp(s->k, k, sizeof(double) * nsite);
+        cp(s->row_site, s->h_drude_site.data(), sizeof(int32_t) * s->nd);
+        cp(s->row_qs, row_qs.data(), sizeof(double) * s->nd);
+        cp(s->row_k, row_k.data(), sizeof(double) * s->nd);
+        cp(s->exA_lo, exA_lo.data(), sizeof(int32_t) * s->nd_pad);
+        cp(s->exA_len, exA_len.data(), sizeof(int32_t) * s->nd_pad);
+        cp(s->exB_lo, exB_lo.data(), sizeof(int32_t) * s->nd_pad);
+        cp(s->exB_len, exB_len.data(), sizeof(int32_t) * s->nd_pad);
+        cp(s->th_ptr, th_ptr.data(), sizeof(int32_t) * (s->nd + 1));
+        cp(s->th_row, th_row.data(), sizeof(int32_t) * th_row.size());
+        cp(s->th_u, th_u.data(), sizeof(double) * th_u.size());
+        if (e == cudaSuccess) e = cudaMemset(s->rowx, 0, sizeof(double) * s->nd_pad);
+        if (e == cudaSuccess) e = cudaMemset(s->rowy, 0, sizeof(double) * s->nd_pad);
+        if (e == cudaSuccess) e = cudaMemset(s->rowz, 0, sizeof(double) * s->nd_pad);
+        if (e == cudaSuccess) e = cudaMemset(s->srowx, 0, sizeof(double) * s->nd_pad);
+        if (e == cudaSuccess) e = cudaMemset(s->srowy, 0, sizeof(double) * s->nd_pad);
+        if (e == cudaSuccess) e = cudaMemset(s->srowz, 0, sizeof(double) * s->nd_pad);
+        if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); free_system(s); return UPOL_ERR_CUDA; }
+    }
+    compute_centre(s, r_core);
+    TRY(sys_upload_positions(s, nullptr, 0));
+    if (cudaDeviceSynchronize() != cudaSuccess) { set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__); free_system(s); return UPOL_ERR_CUDA; }
+#undef TRY
+    *out = s;
+    return UPOL_OK;
+}
+
+int upol_system_destroy(upol_system *s) {
+    if (!s) return UPOL_OK;
+    DeviceGuard guard(s->device);
+    cudaDeviceSynchronize();
+    free_system(s);
+    return UPOL_OK;
+}
+
+int upol_system_set_positions(upol_system *s, const double *r_core, void *stream) {
+    if (!s || !r_core) return UPOL_ERR_ARG;
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    compute_centre(s, r_core);
+    UPOL_CUDA(cudaMemcpyAsync(s->r, r_core, sizeof(double) * 3 * s->nsite, cudaMemcpyHostToDevice, st));
+    return sys_upload_positions(s, nullptr, st);
+}
+
+int upol_system_set_positions_dev(upol_system *s, const double *r_core_dev, void *stream) {
+    if (!s || !r_core_dev) return UPOL_ERR_ARG;
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // the box centre (used only by the fp32 coordinates of mixed mode) is kept from creation
+    UPOL_CUDA(cudaMemcpyAsync(s->r, r_core_dev, sizeof(double) * 3 * s->nsite, cudaMemcpyDeviceToDevice, st));
+    return sys_upload_positions(s, nullptr, st);
+}
+
+int64_t upol_system_nsite(const upol_system *s) { return s ? s->nsite : 0; }
+int64_t upol_system_ndrude(const upol_system *s) { return s ? s->nd : 0; }
+
+int64_t upol_system_interactions(const upol_system *s, int static_part) {
+    if (!s) return 0;
+    int64_t total = 0;
+    for (int64_t m = s->mol_lo; m < s->mol_hi; ++m) {
+        const int64_t rows = s->h_mol_nrow[m];
+        const int64_t cols = static_part ? (s->nsite - s->h_mol_nsite[m])
+                                         : (s->nsite - s->h_mol_nsite[m]) + (s->nd - s->h_mol_nrow[m]);
+        total += rows * cols;
+    }
+    return total;
+}
+
+int upol_system_set_row_range(upol_system *s, int64_t mol_lo, int64_t mol_hi) {
+    if (!s || mol_lo < 0 || mol_hi > s->nmol || mol_lo > mol_hi) return UPOL_ERR_ARG;
+    s->mol_lo = mol_lo; s->mol_hi = mol_hi;
+    s->row_lo = mol_lo < s->nmol ? s->h_mol_row0[mol_lo] : s->nd;
+    s->row_hi = mol_hi < s->nmol ? s->h_mol_row0[mol_hi] : s->nd;
+    s->static_valid = false;
+    return UPOL_OK;
+}
+
+int upol_uind_energy_grad_dev(upol_system *s, const double *d, int precision, double *energy,
+                              double *grad, void *stream) {
+    if (!s || !d || !energy) return UPOL_ERR_ARG;
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = sys_gather_d(s, d, s->dc, st);
+    if (rc) return rc;
+    EvalOpts o;
+    o.precision = precision;
+    o.want_grad = grad != nullptr;
+    rc = sys_eval_compact(s, s->dc, o, energy, s->gc, st);
+    if (rc) return rc;
+    if (grad) {
+        if (s->nranks > 1) { rc = comm_allgather_rows(s, s->gc, st); if (rc) return rc; }
+        rc = sys_scatter_g(s, s->gc, grad, st);
+    }
+    return rc;
+}
+
+int upol_uind_energy_grad_host(upol_system *s, const double *d, int precision, double *energy, double *grad) {
+    if (!s || !d || !energy) return UPOL_ERR_ARG;
+    DeviceGuard guard(s->device);
+    const size_t n3 = 3 * (size_t)s->nsite;
+    int rc = sys_ensure_pinned(s, sizeof(double) * (2 * n3 + UPOL_E_SIZE));
+    if (rc) return rc;
+    // device scratch for the full-layout d and grad
+    double *dfull = nullptr;
+    UPOL_CUDA(cudaMalloc((void **)&dfull, sizeof(double) * (2 * n3 + UPOL_E_SIZE)));
+    double *gfull = dfull + n3, *e_dev = gfull + n3;
+    double *pd = s->pin, *pg = s->pin + n3, *pe = pg + n3;
+    memcpy(pd, d, sizeof(double) * n3);
+    cudaStream_t st = 0;
+    cudaError_t e = cudaMemcpyAsync(dfull, pd, sizeof(double) * n3, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        rc = upol_uind_energy_grad_dev(s, dfull, precision, e_dev, grad ? gfull : nullptr, st);
+        if (rc == UPOL_OK) {
+            e = cudaMemcpyAsync(pe, e_dev, sizeof(double) * UPOL_E_SIZE, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && grad) e = cudaMemcpyAsync(pg, gfull, sizeof(double) * n3, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+    }
+    cudaFree(dfull);
+    if (rc) return rc;
+    if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
+    memcpy(energy, pe, sizeof(double) * UPOL_E_SIZE);
+    if (grad) memcpy(grad, pg, sizeof(double) * n3);
+    return UPOL_OK;
+}
+
+int upol_coulomb_static_dev(upol_system *s, double *out2, void *stream) {
+    if (!s || !out2) return UPOL_ERR_ARG;
+    DeviceGuard guard(s->device);
+    return sys_coulomb_static(s, out2, (cudaStream_t)stream);
+}
+
+int upol_make_sij_dev(const double *rij, const double *u, int u_is_scalar, int64_t n, double *out, void *stream) {
+    if (!rij || !u || !out || n < 0) return UPOL_ERR_ARG;
+    return sys_make_sij(rij, u, u_is_scalar, n, out, (cudaStream_t)stream);
+}
+
+void upol_min_options_default(upol_min_options *o) {
+    if (!o) return;
+    o->tol = 1e-4;          // polarization.py:178
+    o->maxiter = 500;       // jaxopt default
+    o->method = UPOL_LBFGS;
+    o->precision = UPOL_FP64;
+    o->history = 8;
+    o->check_every = 4;
+    o->reserved = 0;
+}
+
+int upol_minimize_dev(upol_system *s, double *d, const upol_min_options *opts, upol_min_result *res, void *stream) {
+    if (!s || !d || !res) return UPOL_ERR_ARG;
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    upol_min_options o;
+    if (opts) o = *opts; else upol_min_options_default(&o);
+    int rc = sys_gather_d(s, d, s->dc, st);
+    if (rc) return rc;
+    rc = minimize_compact(s, s->dc, &o, res, st);
+    if (rc < 0) return rc;
+    int rc2 = sys_scatter_d(s, s->dc, d, st);
+    if (rc2) return rc2;
+    UPOL_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+int upol_minimize_host(upol_system *s, double *d, const upol_min_options *opts, upol_min_result *res) {
+    if (!s || !d || !res) return UPOL_ERR_ARG;
+    DeviceGuard guard(s->device);
+    const size_t n3 = 3 * (size_t)s->nsite;
+    int rc = sys_ensure_pinned(s, sizeof(double) * n3);
+    if (rc) return rc;
+    double *dfull = nullptr;
+    UPOL_CUDA(cudaMalloc((void **)&dfull, sizeof(double) * n3));
+    memcpy(s->pin, d, sizeof(double) * n3);
+    cudaError_t e = cudaMemcpyAsync(dfull, s->pin, sizeof(double) * n3, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess) {
+        rc = upol_minimize_dev(s, dfull, opts, res, 0);
+        if (rc >= 0) {
+            e = cudaMemcpyAsync(s->pin, dfull, sizeof(double) * n3, cudaMemcpyDeviceToHost, 0);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+        }
+    }
+    cudaFree(dfull);
+    if (rc < 0) return rc;
+    if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
+    memcpy(d, s->pin, sizeof(double) * n3);
+    return rc;
+}
+
+}  // extern "C"

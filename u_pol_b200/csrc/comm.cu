@@ -1,0 +1,150 @@
+// Multi-GPU plumbing: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+// The reference has no distributed code at all; this is new: rows are
+// sharded by molecule blocks, columns replicated, so one evaluation needs an all-reduce of the
+// small energy/scalar pack and an all-gather of the row-sliced vectors (d or grad).
+//
+// NCCL is bound at run time with dlopen("libnccl.so.2") - the library PyTorch already loaded in
+// the same process - so libupol_b200.so has no link-time NCCL dependency and loads on a
+// CPU-only host for the symbol checks.
+#include <dlfcn.h>
+
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace upol {
+
+namespace {
+
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat64 = 8 };
+enum { ncclSum = 0 };
+
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    bool ok = false;
+};
+
+NcclApi &api() {
+    static NcclApi a;
+    static bool tried = false;
+    if (tried) return a;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (a.handle) break;
+    }
+    if (!a.handle) return a;
+#define LOAD(field, sym) *(void **)(&a.field) = dlsym(a.handle, sym)
+    LOAD(GetUniqueId, "ncclGetUniqueId");
+    LOAD(CommInitRank, "ncclCommInitRank");
+    LOAD(CommDestroy, "ncclCommDestroy");
+    LOAD(AllReduce, "ncclAllReduce");
+    LOAD(AllGather, "ncclAllGather");
+    LOAD(Broadcast, "ncclBroadcast");
+    LOAD(GroupStart, "ncclGroupStart");
+    LOAD(GroupEnd, "ncclGroupEnd");
+#undef LOAD
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.AllGather &&
+           a.Broadcast && a.GroupStart && a.GroupEnd;
+    return a;
+}
+
+struct CommState {
+    ncclComm_t comm = nullptr;
+    std::vector<int64_t> row_lo, row_hi;   // Drude-row range of every rank
+};
+
+}  // namespace
+
+int comm_allreduce_sum(upol_system *s, double *buf, int64_t n, cudaStream_t st) {
+    if (s->nranks <= 1) return UPOL_OK;
+    CommState *c = static_cast<CommState *>(s->comm);
+    if (!c || !api().ok) return UPOL_ERR_NCCL;
+    return api().AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, c->comm, st) == ncclSuccess ? UPOL_OK : UPOL_ERR_NCCL;
+}
+
+// All-gather of a row-sliced [nd*3] vector, in place: rank g owns rows [row_lo[g], row_hi[g]).
+// Shards are whole molecules and may differ in size by one molecule, so the gather is a group
+// of broadcasts (NCCL fuses a group into one launch).
+int comm_allgather_rows(upol_system *s, double *vec3, cudaStream_t st) {
+    if (s->nranks <= 1) return UPOL_OK;
+    CommState *c = static_cast<CommState *>(s->comm);
+    if (!c || !api().ok) return UPOL_ERR_NCCL;
+    NcclApi &a = api();
+    if (a.GroupStart() != ncclSuccess) return UPOL_ERR_NCCL;
+    for (int g = 0; g < s->nranks; ++g) {
+        const int64_t n = 3 * (c->row_hi[g] - c->row_lo[g]);
+        if (n <= 0) continue;
+        double *p = vec3 + 3 * c->row_lo[g];
+        if (a.Broadcast(p, p, (size_t)n, ncclFloat64, g, c->comm, st) != ncclSuccess) { a.GroupEnd(); return UPOL_ERR_NCCL; }
+    }
+    return a.GroupEnd() == ncclSuccess ? UPOL_OK : UPOL_ERR_NCCL;
+}
+
+void comm_destroy(upol_system *s) {
+    CommState *c = static_cast<CommState *>(s->comm);
+    if (!c) return;
+    if (c->comm && api().ok) api().CommDestroy(c->comm);
+    delete c;
+    s->comm = nullptr;
+    s->nranks = 1; s->rank = 0;
+}
+
+// Balanced molecule blocks: rank g gets molecules [g*nmol/G, (g+1)*nmol/G).
+void shard_bounds(int64_t nmol, int nranks, int rank, int64_t *lo, int64_t *hi) {
+    *lo = nmol * rank / nranks;
+    *hi = nmol * (rank + 1) / nranks;
+}
+
+}  // namespace upol
+
+using namespace upol;
+
+extern "C" int upol_comm_unique_id(unsigned char *id_bytes) {
+    if (!id_bytes) return UPOL_ERR_ARG;
+    if (!api().ok) return UPOL_ERR_NCCL;
+    ncclUniqueId id;
+    if (api().GetUniqueId(&id) != ncclSuccess) return UPOL_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == UPOL_COMM_ID_BYTES, "id size");
+    memcpy(id_bytes, &id, UPOL_COMM_ID_BYTES);
+    return UPOL_OK;
+}
+
+extern "C" int upol_system_attach_comm(upol_system *s, const unsigned char *id_bytes, int rank, int nranks) {
+    if (!s || !id_bytes || nranks < 1 || rank < 0 || rank >= nranks) return UPOL_ERR_ARG;
+    if (!api().ok) return UPOL_ERR_NCCL;
+    comm_destroy(s);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    CommState *c = new CommState();
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, UPOL_COMM_ID_BYTES);
+    int rc = api().CommInitRank(&c->comm, nranks, id, rank);
+    if (prev >= 0) cudaSetDevice(prev);
+    if (rc != ncclSuccess) { delete c; return UPOL_ERR_NCCL; }
+    c->row_lo.resize(nranks); c->row_hi.resize(nranks);
+    for (int g = 0; g < nranks; ++g) {
+        int64_t ml, mh;
+        shard_bounds(s->nmol, nranks, g, &ml, &mh);
+        c->row_lo[g] = ml < s->nmol ? s->h_mol_row0[ml] : s->nd;
+        c->row_hi[g] = mh < s->nmol ? s->h_mol_row0[mh] : s->nd;
+    }
+    s->comm = c; s->rank = rank; s->nranks = nranks;
+    int64_t ml, mh;
+    shard_bounds(s->nmol, nranks, rank, &ml, &mh);
+    return upol_system_set_row_range(s, ml, mh);
+}

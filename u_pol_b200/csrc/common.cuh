@@ -1,0 +1,168 @@
+// Internal declarations shared by the translation units of libupol_b200.so.
+// Not part of the ABI (see include/upol_b200.h for that).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/upol_b200.h"
+
+namespace upol {
+
+// Coulomb constant, U_pol/polarization.py:19-25 (same literals, same operation order).
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kECharge = 1.602176634e-19;
+constexpr double kAvogadro = 6.02214076e23;
+constexpr double kEps0 = 1e-6 * 8.8541878128e-12 / (kECharge * kECharge * kAvogadro);
+constexpr double kCoulomb = 1 / (4 * kPi * kEps0);
+
+// Pair-kernel tiling.  A column tile is kTileCols point charges staged in shared memory;
+// a thread block owns kBlock * ROWS rows (rows live in registers).
+constexpr int kBlock = 128;
+constexpr int kTileCols = 128;
+constexpr int kRowsPerThread = 2;
+constexpr int kRowTile = kBlock * kRowsPerThread;
+constexpr int kPartComps = 5;   // phi_core, phi_shell, Fx, Fy, Fz
+
+#define UPOL_CUDA(expr)                                   \
+    do {                                                  \
+        cudaError_t _e = (expr);                          \
+        if (_e != cudaSuccess) {                          \
+            upol::set_last_cuda_error(_e, __FILE__, __LINE__); \
+            return UPOL_ERR_CUDA;                         \
+        }                                                 \
+    } while (0)
+
+void set_last_cuda_error(cudaError_t e, const char *file, int line);
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// Arguments of one pair-kernel launch (struct passed by value).
+struct PairArgs {
+    // rows
+    int n_rows;                 // rows to process
+    int row0;                   // first row (global row index; shard offset)
+    const double *rx, *ry, *rz; // row positions, global row index
+    const int *exA_lo, *exA_len;  // excluded column interval inside section A (per row)
+    const int *exB_lo, *exB_len;  // excluded column interval inside section B (per row, already offset)
+    // columns: concatenated, each section padded to a multiple of kTileCols
+    const void *cols;           // double4* (fp64) or float4* (mixed): x, y, z, q
+    int n_tiles_a;              // tiles in section A (cores)
+    int n_tiles;                // total tiles (A then B)
+    // output
+    int n_split;                // column splits (gridDim.y)
+    double *part;               // [n_split][kPartComps][part_stride], indexed by LOCAL row
+    int64_t part_stride;
+    // mixed mode only: box centre the float coordinates are relative to
+    double cx, cy, cz;
+    // device-side gate (minimiser): the kernel returns at once when (*gate & gate_skip_mask) != 0
+    const int *gate;
+    int gate_skip_mask;
+};
+
+constexpr int kRowsMixed = 4;
+// gate bits written by the minimiser's control kernel
+constexpr int kGateDone = 1, kGatePhase64 = 2, kGatePhaseMixed = 4;
+
+int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, cudaStream_t st);
+int launch_pair_mixed(const PairArgs &a, cudaStream_t st);
+
+}  // namespace upol
+
+// ------------------------------------------------------------------------------------------
+// The system object behind the opaque handle.
+struct upol_system {
+    int device = 0;
+    int64_t nsite = 0, nmol = 0, nd = 0, npair_ordered = 0;
+    int64_t nd_pad = 0;           // rows padded to kRowTile
+    int64_t na_pad = 0, nb_pad = 0;  // column sections padded to kTileCols
+    int max_split = 0;
+
+    // host-side topology
+    std::vector<int32_t> h_mol, h_drude_site, h_site_row;
+    std::vector<int32_t> h_mol_site0, h_mol_nsite, h_mol_row0, h_mol_nrow;
+    std::vector<double> h_qc, h_qs, h_k;
+
+    // device: per-site parameters and geometry
+    double *r = nullptr;          // [nsite*3] core positions
+    double *qc = nullptr, *qs = nullptr, *k = nullptr;   // [nsite]
+    // device: per-Drude-row (compact)
+    int *row_site = nullptr;      // [nd] site of the row
+    double *row_qs = nullptr, *row_k = nullptr;           // [nd]
+    int *exA_lo = nullptr, *exA_len = nullptr, *exB_lo = nullptr, *exB_len = nullptr;   // [nd_pad]
+    double *rowx = nullptr, *rowy = nullptr, *rowz = nullptr;     // [nd_pad] shell positions
+    double *srowx = nullptr, *srowy = nullptr, *srowz = nullptr;  // [nd_pad] Drude core positions
+    // device: columns
+    double4 *cols = nullptr;      // [na_pad + nb_pad]  cores (x,y,z,qc) | shells (x,y,z,qs)
+    float4 *cols_f = nullptr;     // same, float, relative to the box centre
+    double4 *cols_static = nullptr;  // [na_pad] cores with q = qc + qs/2 (static pass)
+    float *rowx_f = nullptr;      // unused placeholder (rows are converted in-kernel)
+    double centre[3] = {0, 0, 0};
+    // Thole screened pairs as CSR over Drude rows (ordered pairs)
+    int *th_ptr = nullptr;        // [nd+1]
+    int *th_row = nullptr;        // partner row
+    double *th_u = nullptr;
+    // work buffers
+    double *part = nullptr;       // [max_split][kPartComps][nd_pad]
+    double *dc = nullptr;         // [nd*3] compact displacements
+    double *gc = nullptr;         // [nd*3] compact gradient
+    double *eblock = nullptr;     // per-block energy partials
+    int n_eblock = 0;
+    double *energy = nullptr;     // [UPOL_E_SIZE] device result of the last evaluation
+    double *e_static = nullptr;   // [2] device: d-independent part, (value, valid)
+    bool static_valid = false;
+
+    // row shard (Drude rows of molecules [mol_lo, mol_hi))
+    int64_t mol_lo = 0, mol_hi = 0, row_lo = 0, row_hi = 0;
+
+    // pinned host staging for the *_host entry points
+    double *pin = nullptr;
+    size_t pin_bytes = 0;
+
+    // communicator (NCCL), opaque here
+    void *comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    // minimiser workspace (allocated on first use)
+    void *min_ws = nullptr;
+};
+
+namespace upol {
+
+// evaluation pipeline pieces (system.cu / finalize_kernels.cu)
+int sys_prepare_rows(upol_system *s, const double *d_compact, int precision, cudaStream_t st);
+// what one evaluation computes
+struct EvalOpts {
+    int precision = UPOL_FP64;     // arithmetic of the FIELD; the potential is always fp64
+    bool want_energy = true;
+    bool want_grad = true;
+    bool reduce_ranks = true;      // all-reduce the energy vector over ranks (sharded runs)
+    const int *gate = nullptr;     // minimiser gate word (see kGate*)
+    bool phase_switch = false;     // minimiser: launch both field kernels, gate picks one
+};
+int sys_eval_compact(upol_system *s, const double *d_compact, const EvalOpts &o,
+                     double *energy_dev, double *grad_compact, cudaStream_t st);
+int sys_static_part(upol_system *s, cudaStream_t st);
+int sys_gather_d(upol_system *s, const double *d_full, double *d_compact, cudaStream_t st);
+int sys_scatter_g(upol_system *s, const double *g_compact, double *g_full, cudaStream_t st);
+int sys_scatter_d(upol_system *s, const double *d_compact, double *d_full, cudaStream_t st);
+int sys_ensure_pinned(upol_system *s, size_t bytes);
+int choose_split(const upol_system *s, int64_t n_rows, int n_tiles, int rows_per_block);
+int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream_t st);
+int sys_make_sij(const double *rij, const double *u, int u_is_scalar, int64_t n, double *out, cudaStream_t st);
+int sys_coulomb_static(upol_system *s, double *out2, cudaStream_t st);
+const char *last_error_message();
+
+// collectives (comm.cu)
+int comm_allreduce_sum(upol_system *s, double *buf, int64_t n, cudaStream_t st);
+int comm_allgather_rows(upol_system *s, double *vec3, cudaStream_t st);  // [nd*3] in place by shard
+void comm_destroy(upol_system *s);
+
+// minimiser (minimize.cu)
+int minimize_compact(upol_system *s, double *d_compact, const upol_min_options *o,
+                     upol_min_result *res, cudaStream_t st);
+void minimize_free(upol_system *s);
+
+}  // namespace upol

@@ -1,0 +1,64 @@
+// FMA-pipe peak microbenchmarks: the roofline denominators for the pair kernels.
+// MEASURED_PEAKS.json only holds HBM and bf16-GEMM peaks; this path is bound by the FP64 pipe
+// (fp64 mode) or the FP32 FMA pipe (mixed mode), so the denominator is measured on the box with
+// a register-resident chain of independent FMAs (8 accumulators per thread).
+#include "common.cuh"
+
+namespace upol {
+
+template <typename T>
+__global__ void __launch_bounds__(256) fma_chain_kernel(T *out, int iters, T a, T b) {
+    T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+            x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+        }
+    }
+    T s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == (T)-12345.678) out[0] = s;   // never true; keeps the chain alive
+}
+
+template <typename T>
+int measure(double *flops) {
+    T *out = nullptr;
+    UPOL_CUDA(cudaMalloc((void **)&out, sizeof(T)));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256;
+    const int iters = sizeof(T) == 8 ? 4096 : 16384;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        fma_chain_kernel<T><<<blocks, threads>>>(out, iters, (T)1.0000001, (T)1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+        if (rep > 0 && ms > 0.f) best = fl / (ms * 1e-3) > best ? fl / (ms * 1e-3) : best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    UPOL_CUDA(cudaGetLastError());
+    *flops = best;
+    return UPOL_OK;
+}
+
+}  // namespace upol
+
+extern "C" int upol_measure_fma_peak(int device, int use_fp64, double *flops_per_s) {
+    if (!flops_per_s) return UPOL_ERR_ARG;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(device) != cudaSuccess) { upol::set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__); return UPOL_ERR_CUDA; }
+    int rc = use_fp64 ? upol::measure<double>(flops_per_s) : upol::measure<float>(flops_per_s);
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
+}

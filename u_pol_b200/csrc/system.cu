@@ -1,0 +1,502 @@
+// System object: HBM-resident geometry/topology, and the evaluation pipeline
+//   prepare (K4a: shells s = r - d, shell columns) -> pair kernel (K1) -> finalize
+//   (K4b/K2: scale, spring, Thole intra, per-block energy partials) -> reduce.
+// Replaces the array construction of U_pol/util.py:45-279 (compact O(N) form) and the body of
+// Uind (polarization.py:111-151) + its gradient.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace upol {
+
+static thread_local char g_err[256] = "";
+void set_last_cuda_error(cudaError_t e, const char *file, int line) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s:%d", (int)e, cudaGetErrorString(e), file, line);
+}
+const char *last_error_message() { return g_err; }
+
+constexpr double kFar = 1.0e8;   // nm; position of zero-charge padding columns
+
+// ---------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------
+
+// Core columns (section A), static-pass columns and Drude core rows; once per geometry.
+__global__ void build_core_columns_kernel(int nsite, int na_pad, const double *__restrict__ r,
+                                          const double *__restrict__ qc, const double *__restrict__ qs,
+                                          double cx, double cy, double cz,
+                                          double4 *__restrict__ cols, float4 *__restrict__ cols_f,
+                                          double4 *__restrict__ cols_static) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= na_pad) return;
+    if (i < nsite) {
+        const double x = r[3 * i], y = r[3 * i + 1], z = r[3 * i + 2];
+        cols[i] = make_double4(x, y, z, qc[i]);
+        cols_f[i] = make_float4((float)(x - cx), (float)(y - cy), (float)(z - cz), (float)qc[i]);
+        cols_static[i] = make_double4(x, y, z, qc[i] + 0.5 * qs[i]);
+    } else {
+        cols[i] = make_double4(kFar, kFar, kFar, 0.0);
+        cols_f[i] = make_float4((float)kFar, (float)kFar, (float)kFar, 0.f);
+        cols_static[i] = make_double4(kFar, kFar, kFar, 0.0);
+    }
+}
+
+__global__ void build_static_rows_kernel(int nd, const int *__restrict__ row_site, const double *__restrict__ r,
+                                         double *__restrict__ sx, double *__restrict__ sy, double *__restrict__ sz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd) return;
+    const int s = row_site[i];
+    sx[i] = r[3 * s]; sy[i] = r[3 * s + 1]; sz[i] = r[3 * s + 2];
+}
+
+// K4a: shell positions and shell columns (section B) from the current displacements.
+__global__ void prepare_shells_kernel(int nd, int nb_pad, const int *__restrict__ row_site,
+                                      const double *__restrict__ r, const double *__restrict__ dc,
+                                      const double *__restrict__ row_qs,
+                                      double cx, double cy, double cz,
+                                      double *__restrict__ rowx, double *__restrict__ rowy, double *__restrict__ rowz,
+                                      double4 *__restrict__ colsB, float4 *__restrict__ colsB_f) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb_pad) return;
+    if (i < nd) {
+        const int s = row_site[i];
+        const double x = r[3 * s] - dc[3 * i], y = r[3 * s + 1] - dc[3 * i + 1], z = r[3 * s + 2] - dc[3 * i + 2];
+        rowx[i] = x; rowy[i] = y; rowz[i] = z;
+        colsB[i] = make_double4(x, y, z, row_qs[i]);
+        colsB_f[i] = make_float4((float)(x - cx), (float)(y - cy), (float)(z - cz), (float)row_qs[i]);
+    } else {
+        colsB[i] = make_double4(kFar, kFar, kFar, 0.0);
+        colsB_f[i] = make_float4((float)kFar, (float)kFar, (float)kFar, 0.f);
+    }
+}
+
+// Thole-screened pair function g(x) = S(u|x|)/|x| and its gradient coefficient
+// (make_Sij, polarization.py:27-31; used at :94-99).  Zero norm -> 0 (polarization.py:33-37).
+__device__ __forceinline__ void thole_g(double x, double y, double z, double u, double &g, double &c) {
+    const double r2 = x * x + y * y + z * z;
+    if (r2 == 0.0) { g = 0.0; c = 0.0; return; }
+    const double rr = sqrt(r2);
+    const double ex = exp(-u * rr);
+    const double S = 1.0 - (1.0 + 0.5 * rr * u) * ex;
+    const double Sp = 0.5 * u * (1.0 + u * rr) * ex;
+    const double ir = 1.0 / rr;
+    g = S * ir;
+    c = (Sp * ir - S * ir * ir) * ir;     // grad g(x) = c * x
+}
+
+template <int BS>
+__device__ __forceinline__ double block_sum(double v, double *sm) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sm[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < BS / 32; ++k) t += sm[k];
+    }
+    return t;   // valid in thread 0
+}
+
+constexpr int kFinBlock = 128;
+
+// K4b + K2: per Drude row, fold the column-split partials, apply K*qs, add the spring and the
+// intra-molecular Thole pairs, write the gradient row, and emit per-block energy partials.
+__global__ void __launch_bounds__(kFinBlock)
+finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int n_split_mixed,
+                     const int *__restrict__ gate, int phase_switch, const double *__restrict__ part, int64_t stride,
+                     const int *__restrict__ row_site, const double *__restrict__ r,
+                     const double *__restrict__ dc, const double *__restrict__ row_qs,
+                     const double *__restrict__ row_k,
+                     const int *__restrict__ th_ptr, const int *__restrict__ th_row,
+                     const double *__restrict__ th_u,
+                     bool with_grad, double *__restrict__ gc, double *__restrict__ eblock) {
+    __shared__ double sm[kFinBlock / 32];
+    const int gw = gate ? *gate : 0;
+    if (gw & kGateDone) return;
+    // which field kernel ran decides how many column splits hold force partials
+    const int n_split_f = (phase_switch && (gw & kGatePhaseMixed)) ? n_split_mixed : n_split_f64;
+    const int lr = blockIdx.x * kFinBlock + threadIdx.x;
+    double e_inter = 0.0, e_intra = 0.0, e_self = 0.0, g2 = 0.0;
+    if (lr < n_rows) {
+        const int i = row0 + lr;
+        double pa = 0.0, pb = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+        for (int s = 0; s < n_split_pot; ++s) {
+            const double *p = part + (int64_t)s * kPartComps * stride + lr;
+            pa += p[0]; pb += p[stride];
+        }
+        if (with_grad) {
+            for (int s = 0; s < n_split_f; ++s) {
+                const double *p = part + (int64_t)s * kPartComps * stride + lr;
+                fx += p[2 * stride]; fy += p[3 * stride]; fz += p[4 * stride];
+            }
+        }
+        const double qs = row_qs[i], kk = row_k[i];
+        const double dx = dc[3 * i], dy = dc[3 * i + 1], dz = dc[3 * i + 2];
+        e_inter = kCoulomb * qs * (pa + 0.5 * pb);
+        e_self = 0.5 * kk * (dx * dx + dy * dy + dz * dz);
+        double gx = -kCoulomb * qs * fx + kk * dx;
+        double gy = -kCoulomb * qs * fy + kk * dy;
+        double gz = -kCoulomb * qs * fz + kk * dz;
+        const int sa = row_site[i];
+        const double rax = r[3 * sa], ray = r[3 * sa + 1], raz = r[3 * sa + 2];
+        for (int p = th_ptr[i]; p < th_ptr[i + 1]; ++p) {
+            const int b = th_row[p];
+            const double u = th_u[p];
+            const int sb = row_site[b];
+            const double Rx = r[3 * sb] - rax, Ry = r[3 * sb + 1] - ray, Rz = r[3 * sb + 2] - raz;
+            const double bx = dc[3 * b], by = dc[3 * b + 1], bz = dc[3 * b + 2];
+            const double Ax = Rx + dx, Ay = Ry + dy, Az = Rz + dz;          // polarization.py:71
+            const double Bx = Rx - bx, By = Ry - by, Bz = Rz - bz;          // :72
+            const double Cx = Ax - bx, Cy = Ay - by, Cz = Az - bz;          // :73
+            double gR, gA, gB, gC, cR, cA, cB, cC;
+            thole_g(Rx, Ry, Rz, u, gR, cR);
+            thole_g(Ax, Ay, Az, u, gA, cA);
+            thole_g(Bx, By, Bz, u, gB, cB);
+            thole_g(Cx, Cy, Cz, u, gC, cC);
+            const double qq = kCoulomb * qs * row_qs[b];
+            e_intra += 0.5 * qq * (gR - gA - gB + gC);                      // :94-99, :107
+            gx += qq * (cC * Cx - cA * Ax);
+            gy += qq * (cC * Cy - cA * Ay);
+            gz += qq * (cC * Cz - cA * Az);
+        }
+        if (with_grad) {
+            gc[3 * i] = gx; gc[3 * i + 1] = gy; gc[3 * i + 2] = gz;
+            g2 = gx * gx + gy * gy + gz * gz;
+        }
+    }
+    const double s0 = block_sum<kFinBlock>(e_inter, sm);
+    const double s1 = block_sum<kFinBlock>(e_intra, sm);
+    const double s2 = block_sum<kFinBlock>(e_self, sm);
+    const double s3 = block_sum<kFinBlock>(g2, sm);
+    if (threadIdx.x == 0) {
+        double *o = eblock + 4 * (int64_t)blockIdx.x;
+        o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
+    }
+}
+
+// Static pass epilogue: E0 partial = -K sum_rows qs_i * phi_i.
+__global__ void __launch_bounds__(kFinBlock)
+finalize_static_kernel(int n_rows, int row0, int n_split, const double *__restrict__ part, int64_t stride,
+                       const double *__restrict__ row_qs, double *__restrict__ eblock) {
+    __shared__ double sm[kFinBlock / 32];
+    const int lr = blockIdx.x * kFinBlock + threadIdx.x;
+    double e = 0.0;
+    if (lr < n_rows) {
+        double pa = 0.0;
+        for (int s = 0; s < n_split; ++s) pa += part[(int64_t)s * kPartComps * stride + lr];
+        e = -kCoulomb * row_qs[row0 + lr] * pa;
+    }
+    const double s0 = block_sum<kFinBlock>(e, sm);
+    if (threadIdx.x == 0) eblock[blockIdx.x] = s0;
+}
+
+// Ordered (deterministic) sum of the per-block partials.
+__global__ void reduce_blocks_kernel(int nblock, int ncomp, const double *__restrict__ eblock,
+                                     double *__restrict__ out, int out_stride) {
+    __shared__ double sm[256 / 32];
+    for (int c = 0; c < ncomp; ++c) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < nblock; b += 256) v += eblock[(int64_t)b * ncomp + c];
+        const double t = block_sum<256>(v, sm);
+        if (threadIdx.x == 0) out[c * out_stride] = t;
+        __syncthreads();
+    }
+}
+
+// energy vector assembly: e[INTER], e[INTRA], e[SELF], e[GNORM2] hold (all-reduced) partial sums
+__global__ void assemble_energy_kernel(double *__restrict__ e, const double *__restrict__ e_static,
+                                       bool put_static, bool total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (put_static) e[UPOL_E_STATIC] = e_static[0];
+        if (total) e[UPOL_E_UIND] = (e[UPOL_E_INTER] + e[UPOL_E_STATIC] + e[UPOL_E_INTRA]) + e[UPOL_E_SELF];
+    }
+}
+
+__global__ void gather3_kernel(int nd, const int *__restrict__ row_site, const double *__restrict__ full,
+                               double *__restrict__ compact) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd) return;
+    const int s = row_site[i];
+    compact[3 * i] = full[3 * s]; compact[3 * i + 1] = full[3 * s + 1]; compact[3 * i + 2] = full[3 * s + 2];
+}
+
+__global__ void scatter3_kernel(int nd, const int *__restrict__ row_site, const double *__restrict__ compact,
+                                double *__restrict__ full) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nd) return;
+    const int s = row_site[i];
+    full[3 * s] = compact[3 * i]; full[3 * s + 1] = compact[3 * i + 1]; full[3 * s + 2] = compact[3 * i + 2];
+}
+
+// make_Sij on a dense array (polarization.py:27-31)
+__global__ void make_sij_kernel(int64_t n, const double *__restrict__ rij, const double *__restrict__ u,
+                                int u_is_scalar, double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = rij[3 * i], y = rij[3 * i + 1], z = rij[3 * i + 2];
+    const double rr = sqrt(x * x + y * y + z * z);
+    const double uu = u_is_scalar ? u[0] : u[i];
+    out[i] = 1.0 - (1.0 + 0.5 * rr * uu) * exp(-uu * rr);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+
+static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+int choose_split(const upol_system *s, int64_t n_rows, int n_tiles, int rows_per_block) {
+    const int64_t rb = std::max<int64_t>(1, (n_rows + rows_per_block - 1) / rows_per_block);
+    const int64_t target = 148 * 8;
+    int64_t sp = (target + rb - 1) / rb;
+    sp = std::min<int64_t>(sp, n_tiles);
+    sp = std::min<int64_t>(sp, s->max_split);
+    return (int)std::max<int64_t>(1, sp);
+}
+
+static int64_t part_stride_for(int64_t n_rows) { return round_up(std::max<int64_t>(n_rows, 1), 512); }
+
+static PairArgs base_args(const upol_system *s) {
+    PairArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_rows = (int)(s->row_hi - s->row_lo);
+    a.row0 = (int)s->row_lo;
+    a.exA_lo = s->exA_lo; a.exA_len = s->exA_len;
+    a.exB_lo = s->exB_lo; a.exB_len = s->exB_len;
+    a.n_tiles_a = (int)(s->na_pad / kTileCols);
+    a.cx = s->centre[0]; a.cy = s->centre[1]; a.cz = s->centre[2];
+    a.part = s->part;
+    a.part_stride = part_stride_for(a.n_rows);
+    return a;
+}
+
+int sys_static_part(upol_system *s, cudaStream_t st) {
+    // K3: d-independent remainder of (Ucoul - Ucoul_static): the f(R) terms of
+    // polarization.py:82-86 that survive the subtraction of :50-61.
+    PairArgs a = base_args(s);
+    a.rx = s->srowx; a.ry = s->srowy; a.rz = s->srowz;
+    a.cols = s->cols_static;
+    a.n_tiles = a.n_tiles_a;
+    a.n_split = choose_split(s, a.n_rows, a.n_tiles, kRowTile);
+    if (a.n_rows > 0) {
+        int rc = launch_pair_fp64(a, true, false, st);
+        if (rc) return rc;
+        const int nb = (int)nblk(a.n_rows, kFinBlock);
+        finalize_static_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, a.n_split, s->part, a.part_stride,
+                                                         s->row_qs, s->eblock);
+        reduce_blocks_kernel<<<1, 256, 0, st>>>(nb, 1, s->eblock, s->e_static, 1);
+    } else {
+        UPOL_CUDA(cudaMemsetAsync(s->e_static, 0, sizeof(double), st));
+    }
+    UPOL_CUDA(cudaGetLastError());
+    s->static_valid = true;
+    return UPOL_OK;
+}
+
+int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, double *energy_dev,
+                     double *gcmp, cudaStream_t st) {
+    if (o.precision != UPOL_FP64 && o.precision != UPOL_MIXED) return UPOL_ERR_ARG;
+    if (o.want_energy && !s->static_valid) {
+        int rc = sys_static_part(s, st);
+        if (rc) return rc;
+    }
+    if (s->nd > 0) {
+        prepare_shells_kernel<<<nblk(s->nb_pad, 256), 256, 0, st>>>(
+            (int)s->nd, (int)s->nb_pad, s->row_site, s->r, dcmp, s->row_qs,
+            s->centre[0], s->centre[1], s->centre[2], s->rowx, s->rowy, s->rowz,
+            s->cols + s->na_pad, s->cols_f + s->na_pad);
+    }
+    PairArgs a = base_args(s);
+    a.rx = s->rowx; a.ry = s->rowy; a.rz = s->rowz;
+    a.n_tiles = (int)((s->na_pad + s->nb_pad) / kTileCols);
+    a.gate = o.gate;
+    double *e = energy_dev ? energy_dev : s->energy;
+    UPOL_CUDA(cudaMemsetAsync(e, 0, UPOL_E_SIZE * sizeof(double), st));
+    if (a.n_rows > 0) {
+        const int split64 = choose_split(s, a.n_rows, a.n_tiles, kRowTile);
+        const int splitmx = choose_split(s, a.n_rows, a.n_tiles, kBlock * kRowsMixed);
+        int split_pot = 0, split_f64 = 0, split_mx = 0;
+        const bool f64_field = o.want_grad && (o.precision == UPOL_FP64 || o.phase_switch);
+        const bool mx_field = o.want_grad && o.precision == UPOL_MIXED;
+        int rc = UPOL_OK;
+        if (f64_field || o.want_energy) {
+            // fp64 kernel: potential and/or field.  With a mixed field the fp64 launch carries the
+            // potential only (energies are always fp64), unless the minimiser switches phases.
+            PairArgs b = a;
+            b.cols = s->cols;
+            b.n_split = split64;
+            b.gate_skip_mask = kGateDone | (o.phase_switch ? kGatePhaseMixed : 0);
+            rc = launch_pair_fp64(b, o.want_energy, f64_field, st);
+            if (rc) return rc;
+            if (o.want_energy) split_pot = split64;
+            if (f64_field) split_f64 = split64;
+        }
+        if (mx_field) {
+            PairArgs b = a;
+            b.cols = s->cols_f;
+            b.n_split = splitmx;
+            b.gate_skip_mask = kGateDone | (o.phase_switch ? kGatePhase64 : 0);
+            rc = launch_pair_mixed(b, st);
+            if (rc) return rc;
+            split_mx = splitmx;
+            if (!o.phase_switch) split_f64 = splitmx;   // no gate: the mixed partials are THE field
+        }
+        const int nb = (int)nblk(a.n_rows, kFinBlock);
+        finalize_rows_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, split_pot, split_f64, split_mx,
+                                                       o.gate, o.phase_switch ? 1 : 0, s->part, a.part_stride,
+                                                       s->row_site, s->r, dcmp, s->row_qs, s->row_k,
+                                                       s->th_ptr, s->th_row, s->th_u, o.want_grad, gcmp, s->eblock);
+        // eblock comps (inter, intra, self, g2) -> energy[INTER..GNORM2], contiguous by design
+        reduce_blocks_kernel<<<1, 256, 0, st>>>(nb, 4, s->eblock, e + UPOL_E_INTER, 1);
+        UPOL_CUDA(cudaGetLastError());
+    }
+    // static partial of this rank's rows, then (sharded runs) one all-reduce of the vector
+    const bool reduce = o.reduce_ranks && s->nranks > 1;
+    assemble_energy_kernel<<<1, 32, 0, st>>>(e, s->e_static, o.want_energy, !reduce);
+    if (reduce) {
+        int rc = comm_allreduce_sum(s, e, UPOL_E_SIZE, st);
+        if (rc) return rc;
+        assemble_energy_kernel<<<1, 32, 0, st>>>(e, s->e_static, false, true);
+    }
+    UPOL_CUDA(cudaGetLastError());
+    return UPOL_OK;
+}
+
+int sys_gather_d(upol_system *s, const double *d_full, double *d_compact, cudaStream_t st) {
+    if (s->nd == 0) return UPOL_OK;
+    gather3_kernel<<<nblk(s->nd, 256), 256, 0, st>>>((int)s->nd, s->row_site, d_full, d_compact);
+    UPOL_CUDA(cudaGetLastError());
+    return UPOL_OK;
+}
+
+int sys_scatter_g(upol_system *s, const double *g_compact, double *g_full, cudaStream_t st) {
+    // non-polarisable sites: gradient exactly zero
+    UPOL_CUDA(cudaMemsetAsync(g_full, 0, sizeof(double) * 3 * s->nsite, st));
+    if (s->nd == 0) return UPOL_OK;
+    const int64_t n = s->nranks > 1 ? s->nd : (s->row_hi - s->row_lo);
+    const int64_t r0 = s->nranks > 1 ? 0 : s->row_lo;
+    if (n > 0)
+        scatter3_kernel<<<nblk(n, 256), 256, 0, st>>>((int)n, s->row_site + r0, g_compact + 3 * r0, g_full);
+    UPOL_CUDA(cudaGetLastError());
+    return UPOL_OK;
+}
+
+int sys_scatter_d(upol_system *s, const double *d_compact, double *d_full, cudaStream_t st) {
+    if (s->nd == 0) return UPOL_OK;
+    scatter3_kernel<<<nblk(s->nd, 256), 256, 0, st>>>((int)s->nd, s->row_site, d_compact, d_full);
+    UPOL_CUDA(cudaGetLastError());
+    return UPOL_OK;
+}
+
+int sys_ensure_pinned(upol_system *s, size_t bytes) {
+    if (s->pin_bytes >= bytes) return UPOL_OK;
+    if (s->pin) cudaFreeHost(s->pin);
+    s->pin = nullptr; s->pin_bytes = 0;
+    UPOL_CUDA(cudaMallocHost((void **)&s->pin, bytes));
+    s->pin_bytes = bytes;
+    return UPOL_OK;
+}
+
+int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream_t st) {
+    // r already in s->r (device).  Box centre from the host copy is not available for the
+    // device-pointer path, so the centre is computed on the device-free side only when the
+    // host copy is given; here we (re)build the columns with the current centre.
+    (void)r_dev_or_null;
+    build_core_columns_kernel<<<nblk(s->na_pad, 256), 256, 0, st>>>(
+        (int)s->nsite, (int)s->na_pad, s->r, s->qc, s->qs, s->centre[0], s->centre[1], s->centre[2],
+        s->cols, s->cols_f, s->cols_static);
+    if (s->nd > 0)
+        build_static_rows_kernel<<<nblk(s->nd, 256), 256, 0, st>>>((int)s->nd, s->row_site, s->r,
+                                                                    s->srowx, s->srowy, s->srowz);
+    UPOL_CUDA(cudaGetLastError());
+    s->static_valid = false;
+    return UPOL_OK;
+}
+
+int sys_make_sij(const double *rij, const double *u, int u_is_scalar, int64_t n, double *out, cudaStream_t st) {
+    if (n <= 0) return UPOL_OK;
+    make_sij_kernel<<<nblk(n, 256), 256, 0, st>>>(n, rij, u, u_is_scalar, out);
+    UPOL_CUDA(cudaGetLastError());
+    return UPOL_OK;
+}
+
+// d-independent sums for Ucoul / Ucoul_static as separate values (polarization.py:50-61,82):
+// rows = every site, columns = cores carrying q_row-matching charges.
+__global__ void site_rows_kernel(int nsite, const double *__restrict__ r, double *__restrict__ x,
+                                 double *__restrict__ y, double *__restrict__ z) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsite) return;
+    x[i] = r[3 * i]; y[i] = r[3 * i + 1]; z[i] = r[3 * i + 2];
+}
+__global__ void charge_columns_kernel(int nsite, int na_pad, const double *__restrict__ r,
+                                      const double *__restrict__ qc, const double *__restrict__ qs,
+                                      int total, double4 *__restrict__ cols) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= na_pad) return;
+    if (i < nsite) cols[i] = make_double4(r[3 * i], r[3 * i + 1], r[3 * i + 2], total ? qc[i] + qs[i] : qc[i]);
+    else cols[i] = make_double4(kFar, kFar, kFar, 0.0);
+}
+__global__ void __launch_bounds__(kFinBlock)
+finalize_sites_kernel(int nsite, int n_split, const double *__restrict__ part, int64_t stride,
+                      const double *__restrict__ qc, const double *__restrict__ qs, int total,
+                      double *__restrict__ eblock) {
+    __shared__ double sm[kFinBlock / 32];
+    const int i = blockIdx.x * kFinBlock + threadIdx.x;
+    double e = 0.0;
+    if (i < nsite) {
+        double pa = 0.0;
+        for (int s = 0; s < n_split; ++s) pa += part[(int64_t)s * kPartComps * stride + i];
+        e = 0.5 * kCoulomb * (total ? qc[i] + qs[i] : qc[i]) * pa;
+    }
+    const double s0 = block_sum<kFinBlock>(e, sm);
+    if (threadIdx.x == 0) eblock[blockIdx.x] = s0;
+}
+
+int sys_coulomb_static(upol_system *s, double *out2, cudaStream_t st) {
+    // scratch: rows (3*nsite doubles), site exclusion intervals, columns, partials
+    const int64_t n = s->nsite;
+    double *rows = nullptr, *part = nullptr, *eblock = nullptr;
+    int *ex = nullptr;
+    double4 *cols = nullptr;
+    const int ntile = (int)(s->na_pad / kTileCols);
+    const int64_t rb = (n + kRowTile - 1) / kRowTile;
+    int split = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (148 * 8 + rb - 1) / rb));
+    const int64_t stride = part_stride_for(n);
+    const int nb = (int)nblk(n, kFinBlock);
+    UPOL_CUDA(cudaMalloc((void **)&rows, sizeof(double) * 3 * n));
+    UPOL_CUDA(cudaMalloc((void **)&ex, sizeof(int) * 4 * n));
+    UPOL_CUDA(cudaMalloc((void **)&cols, sizeof(double4) * s->na_pad));
+    UPOL_CUDA(cudaMalloc((void **)&part, sizeof(double) * split * kPartComps * stride));
+    UPOL_CUDA(cudaMalloc((void **)&eblock, sizeof(double) * nb));
+    std::vector<int> hex(4 * n, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        const int m = s->h_mol[i];
+        hex[i] = s->h_mol_site0[m]; hex[n + i] = s->h_mol_nsite[m];
+    }
+    UPOL_CUDA(cudaMemcpyAsync(ex, hex.data(), sizeof(int) * 4 * n, cudaMemcpyHostToDevice, st));
+    site_rows_kernel<<<nblk(n, 256), 256, 0, st>>>((int)n, s->r, rows, rows + n, rows + 2 * n);
+    for (int total = 0; total < 2; ++total) {
+        charge_columns_kernel<<<nblk(s->na_pad, 256), 256, 0, st>>>((int)n, (int)s->na_pad, s->r, s->qc, s->qs, total, cols);
+        PairArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n_rows = (int)n; a.row0 = 0;
+        a.rx = rows; a.ry = rows + n; a.rz = rows + 2 * n;
+        a.exA_lo = ex; a.exA_len = ex + n; a.exB_lo = ex + 2 * n; a.exB_len = ex + 3 * n;
+        a.cols = cols; a.n_tiles_a = ntile; a.n_tiles = ntile;
+        a.n_split = split; a.part = part; a.part_stride = stride;
+        int rc = launch_pair_fp64(a, true, false, st);
+        if (rc) return rc;
+        finalize_sites_kernel<<<nb, kFinBlock, 0, st>>>((int)n, split, part, stride, s->qc, s->qs, total, eblock);
+        reduce_blocks_kernel<<<1, 256, 0, st>>>(nb, 1, eblock, out2 + total, 1);
+    }
+    UPOL_CUDA(cudaGetLastError());
+    UPOL_CUDA(cudaStreamSynchronize(st));   // hex (host vector) and the scratch die here
+    cudaFree(rows); cudaFree(ex); cudaFree(cols); cudaFree(part); cudaFree(eblock);
+    return UPOL_OK;
+}
+
+}  // namespace upol

@@ -1,0 +1,210 @@
+"""Scalable host API over the C ABI: compact O(N) inputs, device-resident state.
+
+``UindSystem`` is the added scalable entry of SURVEY 8b: same semantics as the reference's
+``Uind`` / ``drudeOpt`` (U_pol/polarization.py:111-188) without the dense
+(nmol,nmol,natoms,natoms[,3]) tensors of util.py:78-81,271-274.  PyTorch is used for device
+memory and streams only; all arithmetic happens in libupol_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _np(a, dtype):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(a), dtype=dtype)
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise L.UpolError("u_pol_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def thole_pairs_from_blocks(thole_u, natoms):
+    """(nmol, natoms, natoms) symmetric u blocks (tholeMatrix of util.py:219-247) -> unordered
+    site-pair list (a, b, u) with a < b."""
+    th = np.asarray(thole_u, dtype=np.float64)
+    m, a, b = np.nonzero(np.triu(th, 1))
+    return ((m * natoms + a).astype(np.int32), (m * natoms + b).astype(np.int32), th[m, a, b].copy())
+
+
+class UindSystem:
+    """One geometry + parameter set resident in HBM on ``device``.
+
+    r_core (N,3) nm; q_core, q_shell, k (N,); mol_id (N,) non-decreasing; screened pairs as
+    (pair_a, pair_b, pair_u) site-index lists.
+    """
+
+    def __init__(self, r_core, q_core, q_shell, k, mol_id, pair_a=None, pair_b=None, pair_u=None, device=None):
+        _require_cuda()
+        if device is None:
+            idx = torch.cuda.current_device()
+        elif isinstance(device, int):
+            idx = device
+        else:
+            dev = torch.device(device)
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        r = _np(r_core, np.float64).reshape(-1, 3)
+        self.nsite = r.shape[0]
+        qc, qs, kk = (_np(x, np.float64).reshape(-1) for x in (q_core, q_shell, k))
+        mol = _np(mol_id, np.int32).reshape(-1)
+        if not (qc.size == qs.size == kk.size == mol.size == self.nsite):
+            raise ValueError("r_core, q_core, q_shell, k, mol_id disagree on the number of sites")
+        if pair_a is None:
+            pa = pb = np.zeros(0, np.int32)
+            pu = np.zeros(0, np.float64)
+        else:
+            pa, pb, pu = _np(pair_a, np.int32), _np(pair_b, np.int32), _np(pair_u, np.float64)
+        self._keep = (r, qc, qs, kk, mol, pa, pb, pu)
+        h = C.c_void_p()
+        L.check(L.lib().upol_system_create(
+            C.byref(h), self.device.index, self.nsite, r.ctypes.data, qc.ctypes.data, qs.ctypes.data,
+            kk.ctypes.data, mol.ctypes.data, pa.size, pa.ctypes.data, pb.ctypes.data, pu.ctypes.data),
+            "upol_system_create")
+        self._h = h
+        self.ndrude = int(L.lib().upol_system_ndrude(h))
+        self.nmol = int(np.unique(mol).size)
+        self.rank, self.nranks = 0, 1
+
+    # -- construction helpers -------------------------------------------------------------
+    @classmethod
+    def from_compact(cls, r_core, q_core, q_shell, k, thole_u=None, device=None):
+        """Reference-shaped compact arrays: r_core (nmol,natoms,3), q_* and k (nmol,natoms),
+        thole_u (nmol,natoms,natoms) or None."""
+        r = _np(r_core, np.float64)
+        nmol, natoms = r.shape[0], r.shape[1]
+        mol = np.repeat(np.arange(nmol, dtype=np.int32), natoms)
+        pa = pb = pu = None
+        if thole_u is not None and np.any(np.asarray(thole_u) != 0):
+            pa, pb, pu = thole_pairs_from_blocks(thole_u, natoms)
+        return cls(r.reshape(-1, 3), _np(q_core, np.float64).reshape(-1), _np(q_shell, np.float64).reshape(-1),
+                   _np(k, np.float64).reshape(-1), mol, pa, pb, pu, device=device)
+
+    @classmethod
+    def from_drude_system(cls, system, device=None):
+        return cls.from_compact(system.r_core, system.q_core, system.q_shell, system.k, system.thole_u, device=device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib().upol_system_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing -------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev_f64(self, x, n):
+        t = torch.as_tensor(x, dtype=torch.float64) if not isinstance(x, torch.Tensor) else x.to(torch.float64)
+        t = t.to(self.device).reshape(-1).contiguous()
+        if t.numel() != n:
+            raise ValueError(f"expected {n} values, got {t.numel()}")
+        return t
+
+    def interactions(self, static_part=False):
+        return int(L.lib().upol_system_interactions(self._h, int(static_part)))
+
+    def set_positions(self, r_core):
+        if isinstance(r_core, torch.Tensor) and r_core.is_cuda:
+            t = self._dev_f64(r_core, 3 * self.nsite)
+            L.check(L.lib().upol_system_set_positions_dev(self._h, t.data_ptr(), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            r = _np(r_core, np.float64).reshape(-1)
+            L.check(L.lib().upol_system_set_positions(self._h, r.ctypes.data, self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+
+    # -- hot path -------------------------------------------------------------------------
+    def energy_grad(self, d, precision="fp64", want_grad=True):
+        """(energy vector [8] on device, grad (N,3) on device or None).  Asynchronous."""
+        prec = {"fp64": L.FP64, "mixed": L.MIXED}[precision]
+        with torch.cuda.device(self.device):
+            dd = self._dev_f64(d, 3 * self.nsite)
+            e = torch.empty(L.E_SIZE, dtype=torch.float64, device=self.device)
+            g = torch.empty(self.nsite, 3, dtype=torch.float64, device=self.device) if want_grad else None
+            L.check(L.lib().upol_uind_energy_grad_dev(self._h, dd.data_ptr(), prec, e.data_ptr(),
+                                                       g.data_ptr() if want_grad else None, self._stream()),
+                    "upol_uind_energy_grad_dev")
+        return e, g
+
+    def energy_grad_host(self, d, precision="fp64", want_grad=True):
+        """Host-buffer variant (numpy in, numpy out; copies inside the call)."""
+        prec = {"fp64": L.FP64, "mixed": L.MIXED}[precision]
+        dd = _np(d, np.float64).reshape(-1)
+        e = np.empty(L.E_SIZE, np.float64)
+        g = np.empty(3 * self.nsite, np.float64) if want_grad else None
+        L.check(L.lib().upol_uind_energy_grad_host(self._h, dd.ctypes.data, prec, e.ctypes.data,
+                                                    g.ctypes.data if want_grad else None),
+                "upol_uind_energy_grad_host")
+        return e, (g.reshape(self.nsite, 3) if want_grad else None)
+
+    def coulomb_static(self):
+        """(K sum qc qc / R, K sum Q Q / R) over inter-molecular pairs, on device."""
+        with torch.cuda.device(self.device):
+            out = torch.empty(2, dtype=torch.float64, device=self.device)
+            L.check(L.lib().upol_coulomb_static_dev(self._h, out.data_ptr(), self._stream()))
+        return out
+
+    def minimize(self, d0=None, tol=1e-4, maxiter=500, method="lbfgs", precision="fp64", history=8, check_every=4):
+        """Minimise U_ind over the Drude displacements on the device.
+        Returns (d_opt (N,3) device tensor, result dict)."""
+        with torch.cuda.device(self.device):
+            d = torch.zeros(3 * self.nsite, dtype=torch.float64, device=self.device) if d0 is None \
+                else self._dev_f64(d0, 3 * self.nsite).clone()
+            o = L.MinOptions()
+            L.lib().upol_min_options_default(C.byref(o))
+            o.tol, o.maxiter = float(tol), int(maxiter)
+            o.method = {"lbfgs": L.LBFGS, "bfgs": L.LBFGS, "cg": L.CG}[method.lower()]
+            o.precision = {"fp64": L.FP64, "mixed": L.MIXED}[precision]
+            o.history, o.check_every = int(history), int(check_every)
+            res = L.MinResult()
+            rc = L.check(L.lib().upol_minimize_dev(self._h, d.data_ptr(), C.byref(o), C.byref(res), self._stream()),
+                         "upol_minimize_dev")
+        info = {"energy": np.array(res.energy[:]), "U_ind": res.energy[L.E_UIND], "gnorm": res.gnorm,
+                "iterations": res.iterations, "evaluations": res.evaluations, "flags": res.flags, "status": rc}
+        return d.reshape(self.nsite, 3), info
+
+    # -- multi-GPU ------------------------------------------------------------------------
+    def attach_process_group(self, group=None):
+        """Row-shard this system over the ranks of a torch.distributed process group: creates the
+        library's own NCCL communicator (id shipped with torch.distributed) and sets this rank's
+        molecule block."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (C.c_ubyte * L.COMM_ID_BYTES)()
+        if rank == 0:
+            L.check(L.lib().upol_comm_unique_id(buf), "upol_comm_unique_id")
+        ids = [bytes(buf)]
+        dist.broadcast_object_list(ids, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = (C.c_ubyte * L.COMM_ID_BYTES).from_buffer_copy(ids[0])
+        with torch.cuda.device(self.device):
+            L.check(L.lib().upol_system_attach_comm(self._h, raw, rank, world), "upol_system_attach_comm")
+        self.rank, self.nranks = rank, world
+
+    def set_row_range(self, mol_lo, mol_hi):
+        L.check(L.lib().upol_system_set_row_range(self._h, int(mol_lo), int(mol_hi)))
+
+
+def shard_bounds(nmol, nranks, rank):
+    """Molecule block of ``rank`` (same rule as csrc/comm.cu::shard_bounds)."""
+    return nmol * rank // nranks, nmol * (rank + 1) // nranks
+
+
+def measure_fma_peak(fp64=True, device=0):
+    _require_cuda()
+    v = C.c_double()
+    L.check(L.lib().upol_measure_fma_peak(int(device), int(bool(fp64)), C.byref(v)))
+    return v.value

@@ -1,0 +1,182 @@
+"""Drop-in for the hot path of the reference's ``U_pol/polarization.py`` (lines 19-188).
+
+Same names, argument order, shapes and semantics as the reference functions; the arithmetic
+runs in hand-written sm_100a CUDA (``libupol_b200.so``) instead of JAX/XLA + jaxopt:
+
+    set_constants()                                             polarization.py:19-25
+    make_Sij(Rij, u_scale)                                      :27-31
+    Uself(Dij, k)                                               :44-48
+    Ucoul_static(Rij, Qi_shell, Qj_shell, Qi_core, Qj_core)     :50-61
+    Ucoul(Rij, Dij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale)            :63-109
+    Uind(Rij, Dij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k)          :111-151
+    drudeOpt(Rij, Dij0, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k,
+             methods=["BFGS"], d_ref=None)                                    :154-188
+    Uind_and_grad(...)      the value-and-gradient jax.grad produces inside jaxopt (:172-179)
+
+Inputs may be numpy arrays or torch tensors in the reference's dense broadcast layout
+(docstring at :119-135).  They are reduced to the compact O(N) form the kernels use
+(``Rij[0,:,0,:,:]`` is ``r_core`` up to a translation, diagonal blocks of ``u_scale`` are the
+tholeMatrix).  Results come back as 0-d / 1-d torch fp64 tensors on the
+CUDA device (the analogue of the reference's jax arrays); ``float(x)`` / ``.cpu()`` fetches them.
+
+There is no CPU fallback: without the CUDA library or a CUDA device every call raises.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import UindSystem, thole_pairs_from_blocks
+
+logger = logging.getLogger(__name__)
+
+ONE_4PI_EPS0 = None
+
+
+def set_constants():
+    """polarization.py:19-25 - the value comes from the CUDA library so host and kernels agree."""
+    global ONE_4PI_EPS0
+    ONE_4PI_EPS0 = L.lib().upol_one_4pi_eps0()
+    return ONE_4PI_EPS0
+
+
+def _np64(a):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.asarray(a, dtype=np.float64)
+
+
+def _compact(Rij, Qi_shell, Qi_core, u_scale, k=None):
+    """Dense reference tensors -> (r_core (nmol,natoms,3), q_core, q_shell, k, thole blocks)."""
+    R = _np64(Rij)
+    if R.ndim != 5 or R.shape[0] != R.shape[1] or R.shape[2] != R.shape[3] or R.shape[4] != 3:
+        raise ValueError(f"Rij must be (nmol,nmol,natoms,natoms,3), got {R.shape}")
+    nmol, natoms = R.shape[0], R.shape[2]
+    r_core = R[0, :, 0, :, :]                      # r[j,b] - r[0,0]  (util.py:78-81)
+    qs = _np64(Qi_shell).reshape(nmol, natoms)
+    qc = _np64(Qi_core).reshape(nmol, natoms)
+    kk = np.zeros((nmol, natoms)) if k is None else _np64(k).reshape(nmol, natoms)
+    if np.isscalar(u_scale) or np.ndim(u_scale) == 0:
+        if float(u_scale) != 0.0:
+            raise ValueError("a scalar u_scale other than 0.0 is not a reference input (util.py:277)")
+        th = None
+    else:
+        u = _np64(u_scale)
+        idx = np.arange(nmol)
+        th = u[idx, idx]                           # diagonal blocks (util.py:269-274)
+    return r_core, qc, qs, kk, th
+
+
+def _system(Rij, Qi_shell, Qi_core, u_scale, k=None):
+    r_core, qc, qs, kk, th = _compact(Rij, Qi_shell, Qi_core, u_scale, k)
+    return UindSystem.from_compact(r_core, qc, qs, kk, th), r_core.shape[0], r_core.shape[1]
+
+
+def _dij(Dij, nmol, natoms):
+    d = Dij if isinstance(Dij, torch.Tensor) else torch.as_tensor(np.asarray(Dij, dtype=np.float64))
+    if d.numel() != nmol * natoms * 3:
+        raise ValueError(f"Dij must hold {nmol * natoms * 3} values (polarization.py:141-143)")
+    return d.reshape(-1)
+
+
+def make_Sij(Rij, u_scale):
+    """Thole screening function on the dense layout (polarization.py:27-31)."""
+    if not torch.cuda.is_available():
+        raise L.UpolError("u_pol_b200 needs a CUDA device")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    R = torch.as_tensor(_np64(Rij)) if not isinstance(Rij, torch.Tensor) else Rij.to(torch.float64)
+    R = R.to(dev).contiguous()
+    n = R.numel() // 3
+    scalar = np.isscalar(u_scale) or np.ndim(u_scale) == 0
+    if scalar:
+        u = torch.full((1,), float(u_scale), dtype=torch.float64, device=dev)
+    else:
+        u = (torch.as_tensor(_np64(u_scale)) if not isinstance(u_scale, torch.Tensor) else u_scale.to(torch.float64))
+        u = u.to(dev).expand(R.shape[:-1]).contiguous()
+    out = torch.empty(R.shape[:-1], dtype=torch.float64, device=dev)
+    import ctypes as C
+    L.check(L.lib().upol_make_sij_dev(R.data_ptr(), u.data_ptr(), int(scalar), n, out.data_ptr(),
+                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "upol_make_sij_dev")
+    return out
+
+
+def Uself(Dij, k):
+    """1/2 sum k |d|^2 (polarization.py:44-48) - the UPOL_E_SELF component of the device pass."""
+    kk = _np64(k)
+    nmol, natoms = kk.shape
+    # a system of isolated sites: q_core = 0, q_shell = 1 wherever k != 0, far apart molecules
+    # are not needed - the self term does not depend on geometry
+    r = np.zeros((nmol, natoms, 3))
+    r[..., 0] = np.arange(nmol * natoms).reshape(nmol, natoms)
+    sys_ = UindSystem.from_compact(r, np.zeros((nmol, natoms)), (kk != 0).astype(np.float64), kk, None)
+    e, _ = sys_.energy_grad(_dij(Dij, nmol, natoms), want_grad=False)
+    out = e[L.E_SELF].clone()
+    sys_.close()
+    return out
+
+
+def Ucoul_static(Rij, Qi_shell, Qj_shell, Qi_core, Qj_core):
+    """polarization.py:50-61."""
+    sys_, _, _ = _system(Rij, Qi_shell, Qi_core, 0.0)
+    out = sys_.coulomb_static()[1].clone()
+    sys_.close()
+    return out
+
+
+def Ucoul(Rij, Dij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale):
+    """polarization.py:63-109: Ucoul = (Ucoul - Ucoul_static) + Ucoul_static, both on the device."""
+    sys_, nmol, natoms = _system(Rij, Qi_shell, Qi_core, u_scale)
+    e, _ = sys_.energy_grad(_dij(Dij, nmol, natoms), want_grad=False)
+    stat = sys_.coulomb_static()
+    out = (e[L.E_INTER] + e[L.E_STATIC] + e[L.E_INTRA]) + stat[1]
+    sys_.close()
+    return out
+
+
+def Uind(Rij, Dij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k):
+    """polarization.py:111-151 - total induction energy, 0-d fp64 tensor on the device."""
+    sys_, nmol, natoms = _system(Rij, Qi_shell, Qi_core, u_scale, k)
+    e, _ = sys_.energy_grad(_dij(Dij, nmol, natoms), want_grad=False)
+    out = e[L.E_UIND].clone()
+    sys_.close()
+    return out
+
+
+def Uind_and_grad(Rij, Dij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k, precision="fp64"):
+    """(Uind, dUind/dDij) - what ``jax.value_and_grad(Uind, argnums=1)`` yields inside
+    jaxopt.BFGS (polarization.py:172-179); the gradient has the shape of ``Dij``."""
+    sys_, nmol, natoms = _system(Rij, Qi_shell, Qi_core, u_scale, k)
+    e, g = sys_.energy_grad(_dij(Dij, nmol, natoms), precision=precision)
+    shape = tuple(Dij.shape) if hasattr(Dij, "shape") else (nmol * natoms * 3,)
+    out = (e[L.E_UIND].clone(), g.reshape(shape))
+    sys_.close()
+    return out
+
+
+def drudeOpt(Rij, Dij0, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k, methods=["BFGS"], d_ref=None,
+             tol=0.0001, maxiter=500, precision="fp64"):
+    """polarization.py:154-188 - minimise Uind over the Drude displacements, returns ``d_opt``
+    with the shape of ``Dij0`` (the reference passes, and gets back, the flat (3N,) vector).
+
+    ``methods``/``d_ref`` are kept for signature compatibility (vestigial in the reference too).
+    The minimiser is the device-resident L-BFGS (stop rule ||grad||_2 <= tol as jaxopt.BFGS,
+    tol=1e-4 at :178); "BFGS" maps to it, "CG" selects the preconditioned conjugate gradient."""
+    sys_, nmol, natoms = _system(Rij, Qi_shell, Qi_core, u_scale, k)
+    d_opt = None
+    for method in methods:
+        m = {"BFGS": "lbfgs", "LBFGS": "lbfgs", "L-BFGS": "lbfgs", "CG": "cg"}.get(str(method).upper(), "lbfgs")
+        d_opt, info = sys_.minimize(_dij(Dij0, nmol, natoms), tol=tol, maxiter=maxiter, method=m, precision=precision)
+        logger.info("U_POL_B200.%s: %d iterations, %d evaluations, |g| = %.3e",
+                    m.upper(), info["iterations"], info["evaluations"], info["gnorm"])
+        if d_ref is not None:
+            try:
+                if d_ref.any():
+                    _ = torch.linalg.norm(torch.as_tensor(_np64(d_ref)).reshape(-1).to(d_opt.device) - d_opt.reshape(-1))
+            except AttributeError:
+                pass
+    sys_.close()
+    shape = tuple(Dij0.shape) if hasattr(Dij0, "shape") else (nmol * natoms * 3,)
+    return d_opt.reshape(shape)
