@@ -110,8 +110,11 @@ int upol_system_set_row_range(upol_system *sys, int64_t mol_lo, int64_t mol_hi);
  * jax.grad(Uind, argnums=1) taken inside jaxopt.BFGS (polarization.py:172-179).
  *   d[nsite*3]      Drude displacements, reference layout (values on non-polarisable sites are
  *                   ignored, as in the reference where they multiply a zero shell charge)
- *   energy[UPOL_E_SIZE]
- *   grad[nsite*3]   may be NULL (energy only)
+ *   energy[UPOL_E_SIZE]  may be NULL (gradient only: no potential pass, no static part)
+ *   grad[nsite*3]        may be NULL (energy only)
+ * precision selects the arithmetic of the FIELD (gradient).  The potential (energy) is always
+ * accumulated from fp64 pair terms: U_ind is the small difference U_coul - U_coul_static of two
+ * large sums and fp32 pair terms cannot deliver it to 1e-5 ("mixed mode").
  */
 int upol_uind_energy_grad_dev(upol_system *sys, const double *d, int precision,
                               double *energy, double *grad, void *stream);
@@ -195,6 +198,16 @@ int upol_batched_minimize_dev(int device, int64_t nbatch, int64_t nsite,
                               const double *pair_u,
                               double tol, int32_t maxiter,
                               double *energy_dev, int32_t *iterations_dev, void *stream);
+
+/*
+ * Kernel timing hook for roofline reporting (bench.py): when enabled, every energy/gradient
+ * evaluation brackets its main pair kernel with CUDA events on the launching stream.
+ * upol_system_kernel_time synchronises those events and returns the summed duration in ms and
+ * the number of launches since the last call (and resets the counters).  Up to 256 launches are
+ * kept between two calls.
+ */
+int upol_system_set_kernel_timing(upol_system *sys, int enable);
+int upol_system_kernel_time(upol_system *sys, double *ms_total, int32_t *launches);
 
 /* FMA-pipe peak microbenchmarks used as roofline denominators: returns the
  * measured FLOP/s of a register-resident FMA chain on the current device, fp64 or fp32. */

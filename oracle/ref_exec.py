@@ -101,7 +101,7 @@ class _BFGS:
             t = torch.as_tensor(x.reshape(shape)).clone().requires_grad_(True)
             e = self.fun(t)
             (g,) = torch.autograd.grad(e, t)
-            return float(e), g.numpy().ravel()
+            return float(e.detach()), g.numpy().ravel()
 
         res = minimize(fg, x0.ravel(), jac=True, method="BFGS",
                        options={"gtol": self.tol, "norm": 2, "maxiter": self.maxiter})
@@ -195,4 +195,4 @@ def ref_uind_and_grad(Rij, Dij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k
     args[1] = D
     e = ref.Uind(*args)
     (g,) = torch.autograd.grad(e, D)
-    return float(e), g.numpy()
+    return float(e.detach()), g.numpy()

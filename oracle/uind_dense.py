@@ -115,7 +115,7 @@ def u_ind_and_grad(R, D, qis, qjs, qic, qjc, u, k):
     D = _t(D).clone().requires_grad_(True)
     e = u_ind(R, D, qis, qjs, qic, qjc, u, k)
     (g,) = torch.autograd.grad(e, D)
-    return float(e), g.detach().numpy().reshape(np.asarray(D.detach()).shape)
+    return float(e.detach()), g.detach().numpy().reshape(tuple(D.shape))
 
 
 def minimise(R, D0, qis, qjs, qic, qjc, u, k, gtol=1e-4, maxiter=500):

@@ -11,13 +11,18 @@ sysm = UindSystem.from_drude_system(s)
 D = torch.as_tensor(synth.random_displacements(s, seed=1)).cuda()
 print("fp64 FMA peak %.2f TFLOP/s, fp32 %.2f TFLOP/s" % (measure_fma_peak(True) / 1e12, measure_fma_peak(False) / 1e12))
 inter = sysm.interactions()
-for prec in ("fp64", "mixed"):
-    for _ in range(3): sysm.energy_grad(D, precision=prec)
+gref = None
+for prec, we in (("fp64", True), ("fp64", False), ("mixed", False), ("mixed", True)):
+    for _ in range(3): sysm.energy_grad(D, precision=prec, want_energy=we)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = 10
     e0.record()
-    for _ in range(n): e, g = sysm.energy_grad(D, precision=prec)
+    for _ in range(n): e, g = sysm.energy_grad(D, precision=prec, want_energy=we)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    print(f"{prec}: {ms:.3f} ms/eval  {inter/ms/1e6:.1f} Ginteractions/s  alg {20*inter/ms/1e9:.2f} TFLOP/s  U={float(e[0]):.9f} |g|={float(e[4])**0.5:.6f}")
+    if gref is None: gref = g.clone()
+    err = float((g - gref).abs().max() / gref.abs().max()); err2 = float(torch.linalg.norm(g - gref) / torch.linalg.norm(gref))
+    print(f"{prec} energy={we}: {ms:.3f} ms/eval  {inter/ms/1e6:.1f} Ginteractions/s  alg {20*inter/ms/1e9:.2f} TFLOP/s  grad err max {err:.2e} l2 {err2:.2e}")
+t = time.time(); d, info = sysm.minimize(tol=1e-4); torch.cuda.synchronize(); print("minimise fp64 %.3fs" % (time.time() - t), {k: v for k, v in info.items() if k != "energy"})
+t = time.time(); d, info = sysm.minimize(tol=1e-4, precision="mixed"); torch.cuda.synchronize(); print("minimise mixed %.3fs" % (time.time() - t), {k: v for k, v in info.items() if k != "energy"})

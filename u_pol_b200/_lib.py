@@ -59,6 +59,8 @@ _SIGNATURES = {
     "upol_system_attach_comm": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "upol_batched_minimize_dev": (C.c_int, [C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P,
                                             C.c_double, C.c_int32, _P, _P, _P]),
+    "upol_system_set_kernel_timing": (C.c_int, [_P, C.c_int]),
+    "upol_system_kernel_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "upol_measure_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

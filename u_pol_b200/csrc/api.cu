@@ -1,6 +1,7 @@
 // extern "C" entry points of libupol_b200.so (see include/upol_b200.h for the contract and the
 // reference lines each one replaces).
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -46,10 +47,11 @@ void free_system(upol_system *s) {
     comm_destroy(s);
     void *ptrs[] = {s->r, s->qc, s->qs, s->k, s->row_site, s->row_qs, s->row_k, s->exA_lo, s->exA_len,
                     s->exB_lo, s->exB_len, s->rowx, s->rowy, s->rowz, s->srowx, s->srowy, s->srowz,
-                    s->cols, s->cols_f, s->cols_static, s->th_ptr, s->th_row, s->th_u, s->part, s->dc,
+                    s->cols, s->cols_f, s->mix_slot, s->exM_lo, s->exM_len, s->cols_static, s->th_ptr, s->th_row, s->th_u, s->part, s->dc,
                     s->gc, s->eblock, s->energy, s->e_static};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (s->pin) cudaFreeHost(s->pin);
+    for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
     delete s;
 }
 
@@ -60,7 +62,16 @@ void compute_centre(upol_system *s, const double *r_host) {
             lo[c] = std::min(lo[c], r_host[3 * i + c]);
             hi[c] = std::max(hi[c], r_host[3 * i + c]);
         }
-    for (int c = 0; c < 3; ++c) s->centre[c] = s->nsite ? 0.5 * (lo[c] + hi[c]) : 0.0;
+    double half = 0.0;
+    for (int c = 0; c < 3; ++c) {
+        s->centre[c] = s->nsite ? 0.5 * (lo[c] + hi[c]) : 0.0;
+        half = std::max(half, s->nsite ? 0.5 * (hi[c] - lo[c]) : 0.0);
+    }
+    // fixed-point grid of the mixed kernel: 2^-k nm with (half extent + 1 nm of Drude slack)
+    // inside +-2^29, so coordinate differences fit a 32-bit int with room to spare
+    int e = 0;
+    frexp(half + 1.0, &e);                      // half + 1 < 2^e
+    s->inv_grid = ldexp(1.0, 29 - e);
 }
 
 }  // namespace
@@ -133,14 +144,19 @@ int upol_system_create(upol_system **out, int device, int64_t nsite, const doubl
     s->nd_pad = round_up(std::max<int64_t>(s->nd, 1), 512);
     s->na_pad = round_up(nsite, kTileCols);
     s->nb_pad = round_up(std::max<int64_t>(s->nd, 1), kTileCols);
+    s->nm_pad = round_up(nsite + s->nd, kTileCols);
     s->mol_lo = 0; s->mol_hi = s->nmol; s->row_lo = 0; s->row_hi = s->nd;
 
     // per-row tables
     std::vector<int32_t> exA_lo(s->nd_pad, 0), exA_len(s->nd_pad, 0), exB_lo(s->nd_pad, 0), exB_len(s->nd_pad, 0);
     std::vector<double> row_qs(std::max<int64_t>(s->nd, 1), 0.0), row_k(std::max<int64_t>(s->nd, 1), 0.0);
+    std::vector<int32_t> mix_slot(nsite), exM_lo(s->nd_pad, 0), exM_len(s->nd_pad, 0);
+    for (int64_t i = 0, slot = 0; i < nsite; ++i) { mix_slot[i] = (int32_t)slot; slot += (s->h_site_row[i] >= 0) ? 2 : 1; }
     for (int64_t i = 0; i < s->nd; ++i) {
         const int site = s->h_drude_site[i];
         const int m = site_mol[site];
+        exM_lo[i] = mix_slot[s->h_mol_site0[m]];
+        exM_len[i] = s->h_mol_nsite[m] + s->h_mol_nrow[m];
         exA_lo[i] = s->h_mol_site0[m];
         exA_len[i] = s->h_mol_nsite[m];
         exB_lo[i] = (int32_t)s->na_pad + s->h_mol_row0[m];   // concatenated column index
@@ -185,7 +201,8 @@ int upol_system_create(upol_system **out, int device, int64_t nsite, const doubl
     TRY(dev_alloc(&s->rowx, s->nd_pad)); TRY(dev_alloc(&s->rowy, s->nd_pad)); TRY(dev_alloc(&s->rowz, s->nd_pad));
     TRY(dev_alloc(&s->srowx, s->nd_pad)); TRY(dev_alloc(&s->srowy, s->nd_pad)); TRY(dev_alloc(&s->srowz, s->nd_pad));
     TRY(dev_alloc(&s->cols, s->na_pad + s->nb_pad));
-    TRY(dev_alloc(&s->cols_f, s->na_pad + s->nb_pad));
+    TRY(dev_alloc(&s->cols_f, s->nm_pad));
+    TRY(dev_alloc(&s->mix_slot, nsite)); TRY(dev_alloc(&s->exM_lo, s->nd_pad)); TRY(dev_alloc(&s->exM_len, s->nd_pad));
     TRY(dev_alloc(&s->cols_static, s->na_pad));
     TRY(dev_alloc(&s->th_ptr, s->nd + 1)); TRY(dev_alloc(&s->th_row, th_row.size())); TRY(dev_alloc(&s->th_u, th_u.size()));
     TRY(dev_alloc(&s->part, part_elems));
@@ -210,6 +227,9 @@ int upol_system_create(upol_system **out, int device, int64_t nsite, const doubl
         cp(s->exA_len, exA_len.data(), sizeof(int32_t) * s->nd_pad);
         cp(s->exB_lo, exB_lo.data(), sizeof(int32_t) * s->nd_pad);
         cp(s->exB_len, exB_len.data(), sizeof(int32_t) * s->nd_pad);
+        cp(s->mix_slot, mix_slot.data(), sizeof(int32_t) * nsite);
+        cp(s->exM_lo, exM_lo.data(), sizeof(int32_t) * s->nd_pad);
+        cp(s->exM_len, exM_len.data(), sizeof(int32_t) * s->nd_pad);
         cp(s->th_ptr, th_ptr.data(), sizeof(int32_t) * (s->nd + 1));
         cp(s->th_row, th_row.data(), sizeof(int32_t) * th_row.size());
         cp(s->th_u, th_u.data(), sizeof(double) * th_u.size());
@@ -281,7 +301,7 @@ int upol_system_set_row_range(upol_system *s, int64_t mol_lo, int64_t mol_hi) {
 
 int upol_uind_energy_grad_dev(upol_system *s, const double *d, int precision, double *energy,
                               double *grad, void *stream) {
-    if (!s || !d || !energy) return UPOL_ERR_ARG;
+    if (!s || !d || (!energy && !grad)) return UPOL_ERR_ARG;
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = sys_gather_d(s, d, s->dc, st);
@@ -289,6 +309,7 @@ int upol_uind_energy_grad_dev(upol_system *s, const double *d, int precision, do
     EvalOpts o;
     o.precision = precision;
     o.want_grad = grad != nullptr;
+    o.want_energy = energy != nullptr;      // NULL: field pass only (what a minimiser iteration needs)
     rc = sys_eval_compact(s, s->dc, o, energy, s->gc, st);
     if (rc) return rc;
     if (grad) {
@@ -325,6 +346,34 @@ int upol_uind_energy_grad_host(upol_system *s, const double *d, int precision, d
     if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
     memcpy(energy, pe, sizeof(double) * UPOL_E_SIZE);
     if (grad) memcpy(grad, pg, sizeof(double) * n3);
+    return UPOL_OK;
+}
+
+int upol_system_set_kernel_timing(upol_system *s, int enable) {
+    if (!s) return UPOL_ERR_ARG;
+    DeviceGuard guard(s->device);
+    if (enable && s->tev.empty()) {
+        s->tev.resize(512);
+        for (auto &e : s->tev) UPOL_CUDA(cudaEventCreate(&e));
+    }
+    s->timing = enable != 0;
+    s->tev_used = 0;
+    return UPOL_OK;
+}
+
+int upol_system_kernel_time(upol_system *s, double *ms_total, int32_t *launches) {
+    if (!s || !ms_total || !launches) return UPOL_ERR_ARG;
+    DeviceGuard guard(s->device);
+    double tot = 0.0;
+    for (int i = 0; i + 1 < s->tev_used; i += 2) {
+        UPOL_CUDA(cudaEventSynchronize(s->tev[i + 1]));
+        float ms = 0.f;
+        UPOL_CUDA(cudaEventElapsedTime(&ms, s->tev[i], s->tev[i + 1]));
+        tot += ms;
+    }
+    *ms_total = tot;
+    *launches = s->tev_used / 2;
+    s->tev_used = 0;
     return UPOL_OK;
 }
 

@@ -48,15 +48,15 @@ struct PairArgs {
     const int *exA_lo, *exA_len;  // excluded column interval inside section A (per row)
     const int *exB_lo, *exB_len;  // excluded column interval inside section B (per row, already offset)
     // columns: concatenated, each section padded to a multiple of kTileCols
-    const void *cols;           // double4* (fp64) or float4* (mixed): x, y, z, q
+    const void *cols;           // double4* (fp64): x, y, z, q;  int4* (mixed): fixed-point x, y, z + float q bits
     int n_tiles_a;              // tiles in section A (cores)
     int n_tiles;                // total tiles (A then B)
     // output
     int n_split;                // column splits (gridDim.y)
     double *part;               // [n_split][kPartComps][part_stride], indexed by LOCAL row
     int64_t part_stride;
-    // mixed mode only: box centre the float coordinates are relative to
-    double cx, cy, cz;
+    // mixed mode only: box centre and 1/grid of the fixed-point coordinates
+    double cx, cy, cz, inv_grid;
     // device-side gate (minimiser): the kernel returns at once when (*gate & gate_skip_mask) != 0
     const int *gate;
     int gate_skip_mask;
@@ -96,10 +96,15 @@ struct upol_system {
     double *srowx = nullptr, *srowy = nullptr, *srowz = nullptr;  // [nd_pad] Drude core positions
     // device: columns
     double4 *cols = nullptr;      // [na_pad + nb_pad]  cores (x,y,z,qc) | shells (x,y,z,qs)
-    float4 *cols_f = nullptr;     // same, float, relative to the box centre
+    int4 *cols_f = nullptr;       // [nm_pad] mixed kernel: fixed point about the box centre (+ float q bits),
+                                  // ONE section, core and shell of a site adjacent (see pair_kernels.cu)
+    int *mix_slot = nullptr;      // [nsite] column slot of a site's core in cols_f (its shell is slot+1)
+    int *exM_lo = nullptr, *exM_len = nullptr;   // [nd_pad] excluded interval of a row in cols_f
+    int64_t nm_pad = 0;
     double4 *cols_static = nullptr;  // [na_pad] cores with q = qc + qs/2 (static pass)
     float *rowx_f = nullptr;      // unused placeholder (rows are converted in-kernel)
     double centre[3] = {0, 0, 0};
+    double inv_grid = 1.0;        // fixed-point grid: 1/grid, grid = 2^-k nm so the box fits +-2^30
     // Thole screened pairs as CSR over Drude rows (ordered pairs)
     int *th_ptr = nullptr;        // [nd+1]
     int *th_row = nullptr;        // partner row
@@ -127,6 +132,11 @@ struct upol_system {
 
     // minimiser workspace (allocated on first use)
     void *min_ws = nullptr;
+
+    // optional timing of the main pair kernel (bench.py roofline)
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;   // start/stop pairs
+    int tev_used = 0;
 };
 
 namespace upol {

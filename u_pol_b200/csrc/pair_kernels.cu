@@ -150,20 +150,46 @@ __global__ void __launch_bounds__(kBlock) pair_fp64_kernel(const PairArgs a) {
     }
 }
 
-// Mixed mode (field only): fp32 pair arithmetic on coordinates relative to the box centre,
-// per-tile fp32 partial sums promoted to fp64 accumulators after every tile (kTileCols terms).
-// The potential is NOT formed in fp32: U_ind is the small difference of two large sums
-// (U_coul - U_coul_static), and box-scale fp32 coordinates (ulp ~5e-7 nm) cannot deliver it to
-// 1e-5; see DESIGN.md "mixed mode".  Energies always come from the fp64 kernel.
+// Mixed mode (field only): fixed-point coordinates, fp32 pair arithmetic, fp64 accumulation.
+//
+// Positions are stored as 32-bit fixed point relative to the box centre (grid = 2^-k nm chosen
+// so the box fits in +-2^30).  Coordinate differences are then EXACT integer subtractions on the
+// integer pipe; only the difference is converted to fp32 (rel. error 2^-24 of the difference
+// itself, not of the box size).  This matters: each neighbour site contributes a core and a
+// shell term of opposite sign and ~5e3 kJ/mol/nm each that nearly cancel, so box-scale fp32
+// coordinates (ulp ~5e-7 nm) cost 1e-5 of the net gradient; fixed point keeps it ~1e-6.
+// Pair math (r^2, rsqrt, q/r^3, 3 FMAs) is fp32 in grid units; per-tile fp32 partial sums are
+// promoted to fp64 accumulators after every tile; the factor grid^-2 is applied once at the end.
+//
+// The potential is NOT formed here: U_ind is the small difference of two large sums
+// (U_coul - U_coul_static) and fp32 pair terms cannot deliver it to 1e-5 ("mixed
+// mode").  Energies always come from the fp64 kernel.
+__device__ __forceinline__ float rsqrt_f32(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // bare MUFU.RSQ, no denormal fix-up
+    return y;
+}
+
+// q / r^3 from r^2: MUFU.RSQ seed y (rel. error eps <= 2^-22.9) and a first-order correction of
+// the CUBE, y^3 (1 + 1.5 e) with e = 1 - r2 y^2 = -2 eps + O(eps^2); 4 extra FMA-pipe ops bring the
+// 3 eps ~ 4e-7 error of y^3 down to fp32 rounding level.
+__device__ __forceinline__ float q_over_r3(float q, float r2) {
+    const float y = rsqrt_f32(r2);
+    const float t = r2 * y;
+    const float e = fmaf(-t, y, 1.0f);
+    const float c = fmaf(1.5f, e, 1.0f);
+    return ((q * y) * c) * (y * y);
+}
+
 template <int ROWS>
 __global__ void __launch_bounds__(kBlock) pair_mixed_kernel(const PairArgs a) {
-    __shared__ float4 sh[kTileCols];
+    __shared__ int4 sh[kTileCols];
     if (a.gate != nullptr && (*a.gate & a.gate_skip_mask) != 0) return;
-    const float4 *__restrict__ cols = static_cast<const float4 *>(a.cols);
+    const int4 *__restrict__ cols = static_cast<const int4 *>(a.cols);
 
     const int tid = threadIdx.x;
     const int row_base = blockIdx.x * (kBlock * ROWS) + tid;
-    float sx[ROWS], sy[ROWS], sz[ROWS];
+    int sx[ROWS], sy[ROWS], sz[ROWS];
     int loA[ROWS], lenA[ROWS], loB[ROWS], lenB[ROWS];
     double fx[ROWS], fy[ROWS], fz[ROWS];
 #pragma unroll
@@ -171,7 +197,9 @@ __global__ void __launch_bounds__(kBlock) pair_mixed_kernel(const PairArgs a) {
         const int lr = row_base + r * kBlock;
         const bool live = lr < a.n_rows;
         const int i = a.row0 + (live ? lr : 0);
-        sx[r] = (float)(a.rx[i] - a.cx); sy[r] = (float)(a.ry[i] - a.cy); sz[r] = (float)(a.rz[i] - a.cz);
+        sx[r] = __double2int_rn((a.rx[i] - a.cx) * a.inv_grid);
+        sy[r] = __double2int_rn((a.ry[i] - a.cy) * a.inv_grid);
+        sz[r] = __double2int_rn((a.rz[i] - a.cz) * a.inv_grid);
         loA[r] = a.exA_lo[i]; lenA[r] = a.exA_len[i];
         loB[r] = a.exB_lo[i]; lenB[r] = a.exB_len[i];
         fx[r] = fy[r] = fz[r] = 0.0;
@@ -202,31 +230,31 @@ __global__ void __launch_bounds__(kBlock) pair_mixed_kernel(const PairArgs a) {
         if (__any_sync(0xffffffffu, need)) {
 #pragma unroll 2
             for (int j = 0; j < kTileCols; ++j) {
-                const float4 c = sh[j];
+                const int4 c = sh[j];
+                const float cq = __int_as_float(c.w);
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) {
-                    const float dx = c.x - sx[r], dy = c.y - sy[r], dz = c.z - sz[r];
-                    float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    const bool drop = ((unsigned)(j - lo[r]) < (unsigned)len[r]) || (r2 == 0.f);
-                    const float q = drop ? 0.f : c.w;
-                    r2 = drop ? 1.f : r2;
-                    const float inv = rsqrtf(r2);
-                    const float w = (q * inv) * (inv * inv);
+                    const float dx = (float)(c.x - sx[r]), dy = (float)(c.y - sy[r]), dz = (float)(c.z - sz[r]);
+                    const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, 1.0f)));
+                    const bool drop = (unsigned)(j - lo[r]) < (unsigned)len[r];
+                    const float q = drop ? 0.f : cq;
+                    const float w = q_over_r3(q, r2);
                     gx[r] = fmaf(w, dx, gx[r]); gy[r] = fmaf(w, dy, gy[r]); gz[r] = fmaf(w, dz, gz[r]);
                 }
             }
         } else {
 #pragma unroll 8
             for (int j = 0; j < kTileCols; ++j) {
-                const float4 c = sh[j];
+                const int4 c = sh[j];
+                const float cq = __int_as_float(c.w);
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) {
-                    const float dx = c.x - sx[r], dy = c.y - sy[r], dz = c.z - sz[r];
-                    // different molecules never coincide in a physical system; the clamp only
-                    // keeps the arithmetic finite (1e-10 nm is far below fp32 resolution here)
-                    const float r2 = fmaxf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)), 1e-20f);
-                    const float inv = rsqrtf(r2);
-                    const float w = (c.w * inv) * (inv * inv);
+                    const float dx = (float)(c.x - sx[r]), dy = (float)(c.y - sy[r]), dz = (float)(c.z - sz[r]);
+                    // +1 grid unit^2 (~1e-16 nm^2, < 1e-12 of any physical r^2) keeps 1/r finite for a
+                    // coincident pair, which has dx = dy = dz = 0 exactly and so adds w * 0 = 0
+                    // (zero distance -> term dropped) at no extra instruction
+                    const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, 1.0f)));
+                    const float w = q_over_r3(cq, r2);
                     gx[r] = fmaf(w, dx, gx[r]); gy[r] = fmaf(w, dy, gy[r]); gz[r] = fmaf(w, dz, gz[r]);
                 }
             }
@@ -235,14 +263,15 @@ __global__ void __launch_bounds__(kBlock) pair_mixed_kernel(const PairArgs a) {
         for (int r = 0; r < ROWS; ++r) { fx[r] += (double)gx[r]; fy[r] += (double)gy[r]; fz[r] += (double)gz[r]; }
     }
 
+    const double scale = a.inv_grid * a.inv_grid;     // grid units -> nm^-2
     double *out = a.part + (int64_t)blockIdx.y * kPartComps * a.part_stride;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         const int lr = row_base + r * kBlock;
         if (lr < a.n_rows) {
-            out[2 * a.part_stride + lr] = fx[r];
-            out[3 * a.part_stride + lr] = fy[r];
-            out[4 * a.part_stride + lr] = fz[r];
+            out[2 * a.part_stride + lr] = fx[r] * scale;
+            out[3 * a.part_stride + lr] = fy[r] * scale;
+            out[4 * a.part_stride + lr] = fz[r] * scale;
         }
     }
 }

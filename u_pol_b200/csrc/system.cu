@@ -24,22 +24,30 @@ constexpr double kFar = 1.0e8;   // nm; position of zero-charge padding columns
 // small kernels
 // ---------------------------------------------------------------------------------------
 
+constexpr int kFixFar = (1 << 30) - 1;   // fixed-point position of zero-charge padding columns
+
+__device__ __forceinline__ int4 fix_col(double x, double y, double z, double inv_grid, double q) {
+    return make_int4(__double2int_rn(x * inv_grid), __double2int_rn(y * inv_grid), __double2int_rn(z * inv_grid),
+                     __float_as_int((float)q));
+}
+
 // Core columns (section A), static-pass columns and Drude core rows; once per geometry.
 __global__ void build_core_columns_kernel(int nsite, int na_pad, const double *__restrict__ r,
                                           const double *__restrict__ qc, const double *__restrict__ qs,
-                                          double cx, double cy, double cz,
-                                          double4 *__restrict__ cols, float4 *__restrict__ cols_f,
+                                          double cx, double cy, double cz, double inv_grid,
+                                          const int *__restrict__ mix_slot, int n_mix, int nm_pad,
+                                          double4 *__restrict__ cols, int4 *__restrict__ cols_f,
                                           double4 *__restrict__ cols_static) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nm_pad - n_mix) cols_f[n_mix + i] = make_int4(kFixFar, kFixFar, kFixFar, 0);   // tail padding
     if (i >= na_pad) return;
     if (i < nsite) {
         const double x = r[3 * i], y = r[3 * i + 1], z = r[3 * i + 2];
         cols[i] = make_double4(x, y, z, qc[i]);
-        cols_f[i] = make_float4((float)(x - cx), (float)(y - cy), (float)(z - cz), (float)qc[i]);
+        cols_f[mix_slot[i]] = fix_col(x - cx, y - cy, z - cz, inv_grid, qc[i]);
         cols_static[i] = make_double4(x, y, z, qc[i] + 0.5 * qs[i]);
     } else {
         cols[i] = make_double4(kFar, kFar, kFar, 0.0);
-        cols_f[i] = make_float4((float)kFar, (float)kFar, (float)kFar, 0.f);
         cols_static[i] = make_double4(kFar, kFar, kFar, 0.0);
     }
 }
@@ -56,9 +64,10 @@ __global__ void build_static_rows_kernel(int nd, const int *__restrict__ row_sit
 __global__ void prepare_shells_kernel(int nd, int nb_pad, const int *__restrict__ row_site,
                                       const double *__restrict__ r, const double *__restrict__ dc,
                                       const double *__restrict__ row_qs,
-                                      double cx, double cy, double cz,
+                                      double cx, double cy, double cz, double inv_grid,
+                                      const int *__restrict__ mix_slot,
                                       double *__restrict__ rowx, double *__restrict__ rowy, double *__restrict__ rowz,
-                                      double4 *__restrict__ colsB, float4 *__restrict__ colsB_f) {
+                                      double4 *__restrict__ colsB, int4 *__restrict__ cols_f) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb_pad) return;
     if (i < nd) {
@@ -66,10 +75,9 @@ __global__ void prepare_shells_kernel(int nd, int nb_pad, const int *__restrict_
         const double x = r[3 * s] - dc[3 * i], y = r[3 * s + 1] - dc[3 * i + 1], z = r[3 * s + 2] - dc[3 * i + 2];
         rowx[i] = x; rowy[i] = y; rowz[i] = z;
         colsB[i] = make_double4(x, y, z, row_qs[i]);
-        colsB_f[i] = make_float4((float)(x - cx), (float)(y - cy), (float)(z - cz), (float)row_qs[i]);
+        cols_f[mix_slot[s] + 1] = fix_col(x - cx, y - cy, z - cz, inv_grid, row_qs[i]);
     } else {
         colsB[i] = make_double4(kFar, kFar, kFar, 0.0);
-        colsB_f[i] = make_float4((float)kFar, (float)kFar, (float)kFar, 0.f);
     }
 }
 
@@ -269,6 +277,7 @@ static PairArgs base_args(const upol_system *s) {
     a.exB_lo = s->exB_lo; a.exB_len = s->exB_len;
     a.n_tiles_a = (int)(s->na_pad / kTileCols);
     a.cx = s->centre[0]; a.cy = s->centre[1]; a.cz = s->centre[2];
+    a.inv_grid = s->inv_grid;
     a.part = s->part;
     a.part_stride = part_stride_for(a.n_rows);
     return a;
@@ -307,8 +316,8 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
     if (s->nd > 0) {
         prepare_shells_kernel<<<nblk(s->nb_pad, 256), 256, 0, st>>>(
             (int)s->nd, (int)s->nb_pad, s->row_site, s->r, dcmp, s->row_qs,
-            s->centre[0], s->centre[1], s->centre[2], s->rowx, s->rowy, s->rowz,
-            s->cols + s->na_pad, s->cols_f + s->na_pad);
+            s->centre[0], s->centre[1], s->centre[2], s->inv_grid, s->mix_slot, s->rowx, s->rowy, s->rowz,
+            s->cols + s->na_pad, s->cols_f);
     }
     PairArgs a = base_args(s);
     a.rx = s->rowx; a.ry = s->rowy; a.rz = s->rowz;
@@ -330,17 +339,25 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
             b.cols = s->cols;
             b.n_split = split64;
             b.gate_skip_mask = kGateDone | (o.phase_switch ? kGatePhaseMixed : 0);
+            const bool timed = s->timing && s->tev_used + 2 <= (int)s->tev.size();
+            if (timed) cudaEventRecord(s->tev[s->tev_used], st);
             rc = launch_pair_fp64(b, o.want_energy, f64_field, st);
+            if (timed) { cudaEventRecord(s->tev[s->tev_used + 1], st); s->tev_used += 2; }
             if (rc) return rc;
             if (o.want_energy) split_pot = split64;
             if (f64_field) split_f64 = split64;
         }
         if (mx_field) {
             PairArgs b = a;
-            b.cols = s->cols_f;
+            b.cols = s->cols_f;                       // one section: core and shell of a site adjacent
+            b.n_tiles = b.n_tiles_a = (int)(s->nm_pad / kTileCols);
+            b.exA_lo = s->exM_lo; b.exA_len = s->exM_len;
             b.n_split = splitmx;
             b.gate_skip_mask = kGateDone | (o.phase_switch ? kGatePhase64 : 0);
+            const bool timed = s->timing && !(f64_field || o.want_energy) && s->tev_used + 2 <= (int)s->tev.size();
+            if (timed) cudaEventRecord(s->tev[s->tev_used], st);
             rc = launch_pair_mixed(b, st);
+            if (timed) { cudaEventRecord(s->tev[s->tev_used + 1], st); s->tev_used += 2; }
             if (rc) return rc;
             split_mx = splitmx;
             if (!o.phase_switch) split_f64 = splitmx;   // no gate: the mixed partials are THE field
@@ -406,9 +423,9 @@ int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream
     // device-pointer path, so the centre is computed on the device-free side only when the
     // host copy is given; here we (re)build the columns with the current centre.
     (void)r_dev_or_null;
-    build_core_columns_kernel<<<nblk(s->na_pad, 256), 256, 0, st>>>(
-        (int)s->nsite, (int)s->na_pad, s->r, s->qc, s->qs, s->centre[0], s->centre[1], s->centre[2],
-        s->cols, s->cols_f, s->cols_static);
+    build_core_columns_kernel<<<nblk(std::max(s->na_pad, s->nm_pad), 256), 256, 0, st>>>(
+        (int)s->nsite, (int)s->na_pad, s->r, s->qc, s->qs, s->centre[0], s->centre[1], s->centre[2], s->inv_grid,
+        s->mix_slot, (int)(s->nsite + s->nd), (int)s->nm_pad, s->cols, s->cols_f, s->cols_static);
     if (s->nd > 0)
         build_static_rows_kernel<<<nblk(s->nd, 256), 256, 0, st>>>((int)s->nd, s->row_site, s->r,
                                                                     s->srowx, s->srowy, s->srowz);

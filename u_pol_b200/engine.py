@@ -127,14 +127,16 @@ class UindSystem:
             torch.cuda.current_stream(self.device).synchronize()
 
     # -- hot path -------------------------------------------------------------------------
-    def energy_grad(self, d, precision="fp64", want_grad=True):
-        """(energy vector [8] on device, grad (N,3) on device or None).  Asynchronous."""
+    def energy_grad(self, d, precision="fp64", want_grad=True, want_energy=True):
+        """(energy vector [8] on device or None, grad (N,3) on device or None).  Asynchronous.
+        ``precision`` is the arithmetic of the gradient; energies are always fp64."""
         prec = {"fp64": L.FP64, "mixed": L.MIXED}[precision]
         with torch.cuda.device(self.device):
             dd = self._dev_f64(d, 3 * self.nsite)
-            e = torch.empty(L.E_SIZE, dtype=torch.float64, device=self.device)
+            e = torch.empty(L.E_SIZE, dtype=torch.float64, device=self.device) if want_energy else None
             g = torch.empty(self.nsite, 3, dtype=torch.float64, device=self.device) if want_grad else None
-            L.check(L.lib().upol_uind_energy_grad_dev(self._h, dd.data_ptr(), prec, e.data_ptr(),
+            L.check(L.lib().upol_uind_energy_grad_dev(self._h, dd.data_ptr(), prec,
+                                                       e.data_ptr() if want_energy else None,
                                                        g.data_ptr() if want_grad else None, self._stream()),
                     "upol_uind_energy_grad_dev")
         return e, g
@@ -176,6 +178,23 @@ class UindSystem:
                 "iterations": res.iterations, "evaluations": res.evaluations, "flags": res.flags, "status": rc}
         return d.reshape(self.nsite, 3), info
 
+    def invalidate_static(self):
+        """Forget the cached d-independent part (as a new geometry would): the next energy
+        evaluation recomputes it.  Used by bench.py so that a timed step does all the work."""
+        L.check(L.lib().upol_system_set_row_range(self._h, *self._mol_range()))
+
+    def _mol_range(self):
+        return getattr(self, "_mrange", (0, self.nmol))
+
+    def set_kernel_timing(self, enable=True):
+        L.check(L.lib().upol_system_set_kernel_timing(self._h, int(enable)))
+
+    def kernel_time(self):
+        """(summed ms, launches) of the main pair kernel since the last call."""
+        ms, n = C.c_double(), C.c_int32()
+        L.check(L.lib().upol_system_kernel_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     # -- multi-GPU ------------------------------------------------------------------------
     def attach_process_group(self, group=None):
         """Row-shard this system over the ranks of a torch.distributed process group: creates the
@@ -193,9 +212,11 @@ class UindSystem:
         with torch.cuda.device(self.device):
             L.check(L.lib().upol_system_attach_comm(self._h, raw, rank, world), "upol_system_attach_comm")
         self.rank, self.nranks = rank, world
+        self._mrange = shard_bounds(self.nmol, world, rank)
 
     def set_row_range(self, mol_lo, mol_hi):
         L.check(L.lib().upol_system_set_row_range(self._h, int(mol_lo), int(mol_hi)))
+        self._mrange = (int(mol_lo), int(mol_hi))
 
 
 def shard_bounds(nmol, nranks, rank):
