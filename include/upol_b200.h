@@ -188,7 +188,9 @@ int upol_system_attach_comm(upol_system *sys, const unsigned char *id_bytes, int
  * loop of wrapper.py:265-316 around drudeOpt): nbatch systems sharing one topology
  * (nsite sites each), one thread block per system, dense BFGS in shared memory.
  *   r_core[nbatch*nsite*3]; d[nbatch*nsite*3] in/out; energy[nbatch*UPOL_E_SIZE];
- *   iterations[nbatch] may be NULL.  DEVICE pointers except the topology arrays (HOST).
+ *   energy[...][6] holds the UPOL_FLAG_* bits of the system; iterations[nbatch] may be NULL.
+ *   DEVICE pointers except the topology arrays (HOST).  At most 32 Drude sites per system (one
+ *   lane per Drude row).  Returns after the batch has finished.
  */
 int upol_batched_minimize_dev(int device, int64_t nbatch, int64_t nsite,
                               const double *r_core_dev, double *d_dev,

@@ -229,3 +229,41 @@ def measure_fma_peak(fp64=True, device=0):
     v = C.c_double()
     L.check(L.lib().upol_measure_fma_peak(int(device), int(bool(fp64)), C.byref(v)))
     return v.value
+
+
+def batched_minimize(r_batch, q_core, q_shell, k, thole_u=None, d0=None, tol=1e-4, maxiter=500, device=None):
+    """Minimise U_ind for a batch of independent small systems sharing one topology, in one launch
+    (one warp per system; replaces the subprocess-per-dimer loop of wrapper.py:265-316).
+
+    r_batch (B, nmol, natoms, 3) nm; q_core, q_shell, k (nmol, natoms); thole_u (nmol, natoms, natoms).
+    Returns (d_opt (B, nmol*natoms, 3), energy (B, 8), iterations (B,)) as CUDA tensors; energy[:, 6]
+    holds the UPOL_FLAG_* bits of each system."""
+    _require_cuda()
+    idx = torch.cuda.current_device() if device is None else int(torch.device(device).index or 0) if not isinstance(device, int) else device
+    dev = torch.device("cuda", idx)
+    r = torch.as_tensor(r_batch, dtype=torch.float64) if not isinstance(r_batch, torch.Tensor) else r_batch.to(torch.float64)
+    if r.dim() != 4 or r.shape[-1] != 3:
+        raise ValueError("r_batch must be (B, nmol, natoms, 3)")
+    B, nmol, natoms = int(r.shape[0]), int(r.shape[1]), int(r.shape[2])
+    nsite = nmol * natoms
+    qc, qs, kk = (_np(a, np.float64).reshape(-1) for a in (q_core, q_shell, k))
+    if not (qc.size == qs.size == kk.size == nsite):
+        raise ValueError("q_core, q_shell, k must be (nmol, natoms)")
+    mol = np.repeat(np.arange(nmol, dtype=np.int32), natoms)
+    if thole_u is not None and np.any(np.asarray(thole_u) != 0):
+        pa, pb, pu = thole_pairs_from_blocks(thole_u, natoms)
+    else:
+        pa = pb = np.zeros(0, np.int32)
+        pu = np.zeros(0, np.float64)
+    with torch.cuda.device(dev):
+        rd = r.to(dev).reshape(B, nsite * 3).contiguous()
+        d = torch.zeros(B, nsite * 3, dtype=torch.float64, device=dev) if d0 is None else \
+            torch.as_tensor(d0, dtype=torch.float64).to(dev).reshape(B, nsite * 3).clone()
+        e = torch.zeros(B, L.E_SIZE, dtype=torch.float64, device=dev)
+        it = torch.zeros(B, dtype=torch.int32, device=dev)
+        L.check(L.lib().upol_batched_minimize_dev(
+            idx, B, nsite, rd.data_ptr(), d.data_ptr(), qc.ctypes.data, qs.ctypes.data, kk.ctypes.data,
+            mol.ctypes.data, pa.size, pa.ctypes.data, pb.ctypes.data, pu.ctypes.data, float(tol), int(maxiter),
+            e.data_ptr(), it.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+            "upol_batched_minimize_dev")
+    return d.reshape(B, nsite, 3), e, it
