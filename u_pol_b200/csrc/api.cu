@@ -189,7 +189,7 @@ int upol_system_create(upol_system **out, int device, int64_t nsite, const doubl
     // with rb row blocks of <= 512 rows, S*stride <= (1184/rb + 1)(512 rb + 511), which the
     // allocation below covers for the full system and for every row shard of it.
     s->max_split = 256;
-    const size_t part_elems = (size_t)kPartComps * ((size_t)148 * 8 * 1024 + (size_t)s->nd_pad + 1024);
+    const size_t part_elems = (size_t)kPartComps * ((size_t)148 * 64 * 1024 + (size_t)s->nd_pad + 1024);
 
     int rc = UPOL_OK;
 #define TRY(x) do { rc = (x); if (rc) { free_system(s); return rc; } } while (0)

@@ -68,6 +68,7 @@ constexpr int kGateDone = 1, kGatePhase64 = 2, kGatePhaseMixed = 4;
 
 int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, cudaStream_t st);
 int launch_pair_mixed(const PairArgs &a, cudaStream_t st);
+int fp64_rows_per_block();
 
 }  // namespace upol
 

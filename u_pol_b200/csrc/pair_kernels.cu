@@ -22,6 +22,8 @@
 // split) writes its partial sums once - no atomics, deterministic.
 //
 // Zero-distance pairs contribute nothing (polarization.py:33-42).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace upol {
@@ -38,8 +40,8 @@ __device__ __forceinline__ double rsqrt_f64(double x) {
     return fma(q, p, y);
 }
 
-template <int ROWS, bool POT, bool GRAD>
-__global__ void __launch_bounds__(kBlock) pair_fp64_kernel(const PairArgs a) {
+template <int ROWS, bool POT, bool GRAD, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs a) {
     __shared__ double4 sh[kTileCols];
     if (a.gate != nullptr && (*a.gate & a.gate_skip_mask) != 0) return;   // minimiser: converged / other phase
     const double4 *__restrict__ cols = static_cast<const double4 *>(a.cols);
@@ -276,15 +278,25 @@ __global__ void __launch_bounds__(kBlock) pair_mixed_kernel(const PairArgs a) {
     }
 }
 
+template <int ROWS, int MINB>
+static void launch_fp64_variant(const PairArgs &a, bool with_pot, bool with_grad, cudaStream_t st) {
+    dim3 grid((unsigned)((a.n_rows + kBlock * ROWS - 1) / (kBlock * ROWS)), (unsigned)a.n_split);
+    if (with_pot && with_grad)
+        pair_fp64_kernel<ROWS, true, true, MINB><<<grid, kBlock, 0, st>>>(a);
+    else if (with_grad)
+        pair_fp64_kernel<ROWS, false, true, MINB><<<grid, kBlock, 0, st>>>(a);
+    else
+        pair_fp64_kernel<ROWS, true, false, MINB><<<grid, kBlock, 0, st>>>(a);
+}
+
+int fp64_rows_per_block() { return kRowTile; }
+
+// Variants tried on the 100 k-Drude box (profiles/r01_variant_sweep.txt): 1/2/3/4 rows per thread,
+// min-blocks 1/3/4/6/8 - all within 5 %; occupancy is not the limiter (the FP64 pipe is, ~80 %
+// busy), so the plain 2-rows / no-min-blocks build stays.
 int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, cudaStream_t st) {
     if (a.n_rows <= 0) return UPOL_OK;
-    dim3 grid((unsigned)((a.n_rows + kRowTile - 1) / kRowTile), (unsigned)a.n_split);
-    if (with_pot && with_grad)
-        pair_fp64_kernel<kRowsPerThread, true, true><<<grid, kBlock, 0, st>>>(a);
-    else if (with_grad)
-        pair_fp64_kernel<kRowsPerThread, false, true><<<grid, kBlock, 0, st>>>(a);
-    else
-        pair_fp64_kernel<kRowsPerThread, true, false><<<grid, kBlock, 0, st>>>(a);
+    launch_fp64_variant<kRowsPerThread, 1>(a, with_pot, with_grad, st);
     UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
 }

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -259,7 +260,8 @@ static inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) 
 
 int choose_split(const upol_system *s, int64_t n_rows, int n_tiles, int rows_per_block) {
     const int64_t rb = std::max<int64_t>(1, (n_rows + rows_per_block - 1) / rows_per_block);
-    const int64_t target = 148 * 8;
+    static int64_t target = 0;
+    if (target == 0) { const char *e = getenv("UPOL_SPLIT_TARGET"); target = e ? atoll(e) : 148 * 40; }   // ~8 waves of resident blocks: short tail
     int64_t sp = (target + rb - 1) / rb;
     sp = std::min<int64_t>(sp, n_tiles);
     sp = std::min<int64_t>(sp, s->max_split);
@@ -290,7 +292,7 @@ int sys_static_part(upol_system *s, cudaStream_t st) {
     a.rx = s->srowx; a.ry = s->srowy; a.rz = s->srowz;
     a.cols = s->cols_static;
     a.n_tiles = a.n_tiles_a;
-    a.n_split = choose_split(s, a.n_rows, a.n_tiles, kRowTile);
+    a.n_split = choose_split(s, a.n_rows, a.n_tiles, fp64_rows_per_block());
     if (a.n_rows > 0) {
         int rc = launch_pair_fp64(a, true, false, st);
         if (rc) return rc;
@@ -326,7 +328,7 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
     double *e = energy_dev ? energy_dev : s->energy;
     UPOL_CUDA(cudaMemsetAsync(e, 0, UPOL_E_SIZE * sizeof(double), st));
     if (a.n_rows > 0) {
-        const int split64 = choose_split(s, a.n_rows, a.n_tiles, kRowTile);
+        const int split64 = choose_split(s, a.n_rows, a.n_tiles, fp64_rows_per_block());
         const int splitmx = choose_split(s, a.n_rows, a.n_tiles, kBlock * kRowsMixed);
         int split_pot = 0, split_f64 = 0, split_mx = 0;
         const bool f64_field = o.want_grad && (o.precision == UPOL_FP64 || o.phase_switch);
