@@ -55,11 +55,13 @@ typedef struct upol_system upol_system;   /* one geometry + parameters resident 
 
 /* layout of the energy vector written by the energy/gradient entry points (8 doubles) */
 #define UPOL_E_UIND    0   /* (U_coul - U_coul_static) + U_self      polarization.py:149       */
-#define UPOL_E_INTER   1   /* d-dependent inter-molecular core/shell part                      */
+#define UPOL_E_INTER   1   /* inter-molecular part of (U_coul - U_coul_static); the static
+                              potential is subtracted row by row before the sum (conditioning) */
 #define UPOL_E_INTRA   2   /* Thole-screened intra-molecular part     polarization.py:94-105   */
 #define UPOL_E_SELF    3   /* 1/2 sum k d^2                            polarization.py:44-48    */
 #define UPOL_E_GNORM2  4   /* ||dU/dd||_2^2                                                     */
-#define UPOL_E_STATIC  5   /* d-independent remainder of the static subtraction (:50-61,:82)   */
+#define UPOL_E_STATIC  5   /* informational: the d-independent remainder of the static
+                              subtraction (:50-61,:82) summed on its own; ALREADY inside E_INTER */
 #define UPOL_E_SIZE    8
 
 const char *upol_error_string(int code);

@@ -48,9 +48,10 @@ void free_system(upol_system *s) {
     void *ptrs[] = {s->r, s->qc, s->qs, s->k, s->row_site, s->row_qs, s->row_k, s->exA_lo, s->exA_len,
                     s->exB_lo, s->exB_len, s->rowx, s->rowy, s->rowz, s->srowx, s->srowy, s->srowz,
                     s->cols, s->cols_f, s->mix_slot, s->exM_lo, s->exM_len, s->cols_static, s->th_ptr, s->th_row, s->th_u, s->part, s->dc,
-                    s->gc, s->eblock, s->energy, s->e_static};
+                    s->gc, s->eblock, s->energy, s->e_static, s->phi_static};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (s->pin) cudaFreeHost(s->pin);
+    if (s->hscratch) cudaFree(s->hscratch);
     for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
     delete s;
 }
@@ -209,7 +210,7 @@ int upol_system_create(upol_system **out, int device, int64_t nsite, const doubl
     TRY(dev_alloc(&s->dc, 3 * s->nd)); TRY(dev_alloc(&s->gc, 3 * s->nd));
     s->n_eblock = (int)((std::max<int64_t>(s->nd, nsite) + 127) / 128) + 1;
     TRY(dev_alloc(&s->eblock, 4 * (size_t)s->n_eblock));
-    TRY(dev_alloc(&s->energy, UPOL_E_SIZE)); TRY(dev_alloc(&s->e_static, 2));
+    TRY(dev_alloc(&s->energy, UPOL_E_SIZE)); TRY(dev_alloc(&s->e_static, 2)); TRY(dev_alloc(&s->phi_static, s->nd_pad));
 
     {
         cudaError_t e = cudaSuccess;
@@ -262,8 +263,17 @@ int upol_system_set_positions(upol_system *s, const double *r_core, void *stream
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     compute_centre(s, r_core);
-    UPOL_CUDA(cudaMemcpyAsync(s->r, r_core, sizeof(double) * 3 * s->nsite, cudaMemcpyHostToDevice, st));
-    return sys_upload_positions(s, nullptr, st);
+    // stage through pinned memory so the copy is a true async DMA; the caller's buffer is free on return
+    const size_t n3 = 3 * (size_t)s->nsite;
+    int rc = sys_ensure_pinned(s, sizeof(double) * (2 * n3 + UPOL_E_SIZE));
+    if (rc) return rc;
+    UPOL_CUDA(cudaStreamSynchronize(st));                 // staging buffer may still be in flight
+    memcpy(s->pin, r_core, sizeof(double) * n3);
+    UPOL_CUDA(cudaMemcpyAsync(s->r, s->pin, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
+    rc = sys_upload_positions(s, nullptr, st);
+    if (rc) return rc;
+    UPOL_CUDA(cudaStreamSynchronize(st));                 // pin is reused by the *_host entry points
+    return UPOL_OK;
 }
 
 int upol_system_set_positions_dev(upol_system *s, const double *r_core_dev, void *stream) {
@@ -320,31 +330,24 @@ int upol_uind_energy_grad_dev(upol_system *s, const double *d, int precision, do
 }
 
 int upol_uind_energy_grad_host(upol_system *s, const double *d, int precision, double *energy, double *grad) {
-    if (!s || !d || !energy) return UPOL_ERR_ARG;
+    if (!s || !d || (!energy && !grad)) return UPOL_ERR_ARG;
     DeviceGuard guard(s->device);
     const size_t n3 = 3 * (size_t)s->nsite;
     int rc = sys_ensure_pinned(s, sizeof(double) * (2 * n3 + UPOL_E_SIZE));
     if (rc) return rc;
-    // device scratch for the full-layout d and grad
-    double *dfull = nullptr;
-    UPOL_CUDA(cudaMalloc((void **)&dfull, sizeof(double) * (2 * n3 + UPOL_E_SIZE)));
-    double *gfull = dfull + n3, *e_dev = gfull + n3;
+    rc = sys_ensure_hscratch(s, 2 * n3 + UPOL_E_SIZE);
+    if (rc) return rc;
+    double *dfull = s->hscratch, *gfull = dfull + n3, *e_dev = gfull + n3;
     double *pd = s->pin, *pg = s->pin + n3, *pe = pg + n3;
     memcpy(pd, d, sizeof(double) * n3);
     cudaStream_t st = 0;
-    cudaError_t e = cudaMemcpyAsync(dfull, pd, sizeof(double) * n3, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) {
-        rc = upol_uind_energy_grad_dev(s, dfull, precision, e_dev, grad ? gfull : nullptr, st);
-        if (rc == UPOL_OK) {
-            e = cudaMemcpyAsync(pe, e_dev, sizeof(double) * UPOL_E_SIZE, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess && grad) e = cudaMemcpyAsync(pg, gfull, sizeof(double) * n3, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        }
-    }
-    cudaFree(dfull);
+    UPOL_CUDA(cudaMemcpyAsync(dfull, pd, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
+    rc = upol_uind_energy_grad_dev(s, dfull, precision, energy ? e_dev : nullptr, grad ? gfull : nullptr, st);
     if (rc) return rc;
-    if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
-    memcpy(energy, pe, sizeof(double) * UPOL_E_SIZE);
+    if (energy) UPOL_CUDA(cudaMemcpyAsync(pe, e_dev, sizeof(double) * UPOL_E_SIZE, cudaMemcpyDeviceToHost, st));
+    if (grad) UPOL_CUDA(cudaMemcpyAsync(pg, gfull, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
+    UPOL_CUDA(cudaStreamSynchronize(st));
+    if (energy) memcpy(energy, pe, sizeof(double) * UPOL_E_SIZE);
     if (grad) memcpy(grad, pg, sizeof(double) * n3);
     return UPOL_OK;
 }
@@ -419,22 +422,17 @@ int upol_minimize_host(upol_system *s, double *d, const upol_min_options *opts, 
     if (!s || !d || !res) return UPOL_ERR_ARG;
     DeviceGuard guard(s->device);
     const size_t n3 = 3 * (size_t)s->nsite;
-    int rc = sys_ensure_pinned(s, sizeof(double) * n3);
+    int rc = sys_ensure_pinned(s, sizeof(double) * (2 * n3 + UPOL_E_SIZE));
     if (rc) return rc;
-    double *dfull = nullptr;
-    UPOL_CUDA(cudaMalloc((void **)&dfull, sizeof(double) * n3));
+    rc = sys_ensure_hscratch(s, 2 * n3 + UPOL_E_SIZE);
+    if (rc) return rc;
+    double *dfull = s->hscratch;
     memcpy(s->pin, d, sizeof(double) * n3);
-    cudaError_t e = cudaMemcpyAsync(dfull, s->pin, sizeof(double) * n3, cudaMemcpyHostToDevice, 0);
-    if (e == cudaSuccess) {
-        rc = upol_minimize_dev(s, dfull, opts, res, 0);
-        if (rc >= 0) {
-            e = cudaMemcpyAsync(s->pin, dfull, sizeof(double) * n3, cudaMemcpyDeviceToHost, 0);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-        }
-    }
-    cudaFree(dfull);
+    UPOL_CUDA(cudaMemcpyAsync(dfull, s->pin, sizeof(double) * n3, cudaMemcpyHostToDevice, 0));
+    rc = upol_minimize_dev(s, dfull, opts, res, 0);
     if (rc < 0) return rc;
-    if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
+    UPOL_CUDA(cudaMemcpyAsync(s->pin, dfull, sizeof(double) * n3, cudaMemcpyDeviceToHost, 0));
+    UPOL_CUDA(cudaStreamSynchronize(0));
     memcpy(d, s->pin, sizeof(double) * n3);
     return rc;
 }

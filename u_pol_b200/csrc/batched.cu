@@ -259,9 +259,9 @@ __global__ void batched_bfgs_kernel(BatchTopo t, const double *__restrict__ site
     for (int i = lane; i < n; i += 32) dg[3 * t.row_site[i / 3] + i % 3] = m.x[i];
     if (lane == 0) {
         double *e = energy + sys * UPOL_E_SIZE;
-        e[UPOL_E_INTER] = ei; e[UPOL_E_INTRA] = ea; e[UPOL_E_SELF] = es; e[UPOL_E_STATIC] = est;
+        e[UPOL_E_INTER] = ei + est; e[UPOL_E_INTRA] = ea; e[UPOL_E_SELF] = es; e[UPOL_E_STATIC] = est;
         e[UPOL_E_GNORM2] = gnorm * gnorm;
-        e[UPOL_E_UIND] = (ei + est + ea) + es;
+        e[UPOL_E_UIND] = ((ei + est) + ea) + es;
         e[6] = (double)flags; e[7] = 0.0;
         if (iters) iters[sys] = it;
     }

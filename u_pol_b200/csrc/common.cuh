@@ -117,15 +117,18 @@ struct upol_system {
     double *eblock = nullptr;     // per-block energy partials
     int n_eblock = 0;
     double *energy = nullptr;     // [UPOL_E_SIZE] device result of the last evaluation
-    double *e_static = nullptr;   // [2] device: d-independent part, (value, valid)
+    double *e_static = nullptr;   // [2] device: d-independent part summed over rows (informational)
+    double *phi_static = nullptr; // [nd_pad] device: per-row static potential, subtracted row by row
     bool static_valid = false;
 
     // row shard (Drude rows of molecules [mol_lo, mol_hi))
     int64_t mol_lo = 0, mol_hi = 0, row_lo = 0, row_hi = 0;
 
-    // pinned host staging for the *_host entry points
+    // pinned host staging + device scratch for the *_host entry points (kept between calls)
     double *pin = nullptr;
     size_t pin_bytes = 0;
+    double *hscratch = nullptr;   // device: d_full | g_full | energy
+    size_t hscratch_elems = 0;
 
     // communicator (NCCL), opaque here
     void *comm = nullptr;
@@ -160,6 +163,7 @@ int sys_gather_d(upol_system *s, const double *d_full, double *d_compact, cudaSt
 int sys_scatter_g(upol_system *s, const double *g_compact, double *g_full, cudaStream_t st);
 int sys_scatter_d(upol_system *s, const double *d_compact, double *d_full, cudaStream_t st);
 int sys_ensure_pinned(upol_system *s, size_t bytes);
+int sys_ensure_hscratch(upol_system *s, size_t elems);
 int choose_split(const upol_system *s, int64_t n_rows, int n_tiles, int rows_per_block);
 int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream_t st);
 int sys_make_sij(const double *rij, const double *u, int u_is_scalar, int64_t n, double *out, cudaStream_t st);

@@ -121,7 +121,7 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
                      const double *__restrict__ dc, const double *__restrict__ row_qs,
                      const double *__restrict__ row_k,
                      const int *__restrict__ th_ptr, const int *__restrict__ th_row,
-                     const double *__restrict__ th_u,
+                     const double *__restrict__ th_u, const double *__restrict__ phi_static,
                      bool with_grad, double *__restrict__ gc, double *__restrict__ eblock) {
     __shared__ double sm[kFinBlock / 32];
     const int gw = gate ? *gate : 0;
@@ -145,7 +145,9 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
         }
         const double qs = row_qs[i], kk = row_k[i];
         const double dx = dc[3 * i], dy = dc[3 * i + 1], dz = dc[3 * i + 2];
-        e_inter = kCoulomb * qs * (pa + 0.5 * pb);
+        // (U_coul - U_coul_static) share of the row: static potential removed before the row sum
+        const double ps = phi_static ? phi_static[i] : 0.0;
+        e_inter = kCoulomb * qs * ((pa + 0.5 * pb) - ps);
         e_self = 0.5 * kk * (dx * dx + dy * dy + dz * dz);
         double gx = -kCoulomb * qs * fx + kk * dx;
         double gy = -kCoulomb * qs * fy + kk * dy;
@@ -190,13 +192,18 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
 // Static pass epilogue: E0 partial = -K sum_rows qs_i * phi_i.
 __global__ void __launch_bounds__(kFinBlock)
 finalize_static_kernel(int n_rows, int row0, int n_split, const double *__restrict__ part, int64_t stride,
-                       const double *__restrict__ row_qs, double *__restrict__ eblock) {
+                       const double *__restrict__ row_qs, double *__restrict__ phi_static,
+                       double *__restrict__ eblock) {
     __shared__ double sm[kFinBlock / 32];
     const int lr = blockIdx.x * kFinBlock + threadIdx.x;
     double e = 0.0;
     if (lr < n_rows) {
         double pa = 0.0;
         for (int s = 0; s < n_split; ++s) pa += part[(int64_t)s * kPartComps * stride + lr];
+        // kept PER ROW: the static potential (~1e4 e/nm at 100 k Drudes) is subtracted from the
+        // row's core/shell potential before anything is summed over rows, otherwise U_ind
+        // (~1e5 kJ/mol) would be the difference of two ~1e11 kJ/mol totals
+        phi_static[row0 + lr] = pa;
         e = -kCoulomb * row_qs[row0 + lr] * pa;
     }
     const double s0 = block_sum<kFinBlock>(e, sm);
@@ -220,8 +227,8 @@ __global__ void reduce_blocks_kernel(int nblock, int ncomp, const double *__rest
 __global__ void assemble_energy_kernel(double *__restrict__ e, const double *__restrict__ e_static,
                                        bool put_static, bool total) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        if (put_static) e[UPOL_E_STATIC] = e_static[0];
-        if (total) e[UPOL_E_UIND] = (e[UPOL_E_INTER] + e[UPOL_E_STATIC] + e[UPOL_E_INTRA]) + e[UPOL_E_SELF];
+        if (put_static) e[UPOL_E_STATIC] = e_static[0];      // informational; already inside E_INTER
+        if (total) e[UPOL_E_UIND] = (e[UPOL_E_INTER] + e[UPOL_E_INTRA]) + e[UPOL_E_SELF];
     }
 }
 
@@ -298,7 +305,7 @@ int sys_static_part(upol_system *s, cudaStream_t st) {
         if (rc) return rc;
         const int nb = (int)nblk(a.n_rows, kFinBlock);
         finalize_static_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, a.n_split, s->part, a.part_stride,
-                                                         s->row_qs, s->eblock);
+                                                         s->row_qs, s->phi_static, s->eblock);
         reduce_blocks_kernel<<<1, 256, 0, st>>>(nb, 1, s->eblock, s->e_static, 1);
     } else {
         UPOL_CUDA(cudaMemsetAsync(s->e_static, 0, sizeof(double), st));
@@ -368,7 +375,8 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
         finalize_rows_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, split_pot, split_f64, split_mx,
                                                        o.gate, o.phase_switch ? 1 : 0, s->part, a.part_stride,
                                                        s->row_site, s->r, dcmp, s->row_qs, s->row_k,
-                                                       s->th_ptr, s->th_row, s->th_u, o.want_grad, gcmp, s->eblock);
+                                                       s->th_ptr, s->th_row, s->th_u,
+                                                       o.want_energy ? s->phi_static : nullptr, o.want_grad, gcmp, s->eblock);
         // eblock comps (inter, intra, self, g2) -> energy[INTER..GNORM2], contiguous by design
         reduce_blocks_kernel<<<1, 256, 0, st>>>(nb, 4, s->eblock, e + UPOL_E_INTER, 1);
         UPOL_CUDA(cudaGetLastError());
@@ -417,6 +425,15 @@ int sys_ensure_pinned(upol_system *s, size_t bytes) {
     s->pin = nullptr; s->pin_bytes = 0;
     UPOL_CUDA(cudaMallocHost((void **)&s->pin, bytes));
     s->pin_bytes = bytes;
+    return UPOL_OK;
+}
+
+int sys_ensure_hscratch(upol_system *s, size_t elems) {
+    if (s->hscratch_elems >= elems) return UPOL_OK;
+    if (s->hscratch) cudaFree(s->hscratch);
+    s->hscratch = nullptr; s->hscratch_elems = 0;
+    UPOL_CUDA(cudaMalloc((void **)&s->hscratch, sizeof(double) * elems));
+    s->hscratch_elems = elems;
     return UPOL_OK;
 }
 

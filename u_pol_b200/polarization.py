@@ -131,7 +131,7 @@ def Ucoul(Rij, Dij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale):
     sys_, nmol, natoms = _system(Rij, Qi_shell, Qi_core, u_scale)
     e, _ = sys_.energy_grad(_dij(Dij, nmol, natoms), want_grad=False)
     stat = sys_.coulomb_static()
-    out = (e[L.E_INTER] + e[L.E_STATIC] + e[L.E_INTRA]) + stat[1]
+    out = (e[L.E_INTER] + e[L.E_INTRA]) + stat[1]
     sys_.close()
     return out
 
