@@ -35,9 +35,12 @@ def test_312_dimers_one_launch_vs_reference_csv():
     for i in (0, 17, 150, 311):
         sys_.set_positions(r[i])
         _, info = sys_.minimize(tol=1e-6)
-        assert abs(info["U_ind"] - e[i, 0]) <= 1e-8 * abs(e[i, 0])
+        # far dimers: U_ind ~ 1e-5 kJ/mol is 1e-8 of the static sum it is the remainder of (e[:, 5]);
+        # fp64 round-off of that sum is the floor
+        floor = 1e-14 * abs(e[i, 5])
+        assert abs(info["U_ind"] - e[i, 0]) <= 1e-8 * abs(e[i, 0]) + floor
         ei, _ = sys_.energy_grad(d[i])
-        assert abs(float(ei[0]) - e[i, 0]) <= 1e-10 * abs(e[i, 0]) + 1e-13
+        assert abs(float(ei[0]) - e[i, 0]) <= 1e-10 * abs(e[i, 0]) + floor
 
 
 def test_10k_perturbed_dimers():
@@ -51,7 +54,7 @@ def test_10k_perturbed_dimers():
     for i in (312, 5000, 9999):
         sys_.set_positions(r[i])
         _, info = sys_.minimize(tol=1e-6)
-        assert abs(info["U_ind"] - e[i, 0]) <= 1e-8 * abs(e[i, 0])
+        assert abs(info["U_ind"] - e[i, 0]) <= 1e-8 * abs(e[i, 0]) + 1e-14 * abs(e[i, 5])
 
 
 def test_warm_start_and_water():

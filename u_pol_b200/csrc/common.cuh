@@ -68,6 +68,7 @@ constexpr int kGateDone = 1, kGatePhase64 = 2, kGatePhaseMixed = 4;
 
 int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, cudaStream_t st);
 int launch_pair_mixed(const PairArgs &a, cudaStream_t st);
+int launch_pair_static(const PairArgs &a, cudaStream_t st);
 int fp64_rows_per_block();
 
 }  // namespace upol
@@ -102,7 +103,7 @@ struct upol_system {
     int *mix_slot = nullptr;      // [nsite] column slot of a site's core in cols_f (its shell is slot+1)
     int *exM_lo = nullptr, *exM_len = nullptr;   // [nd_pad] excluded interval of a row in cols_f
     int64_t nm_pad = 0;
-    double4 *cols_static = nullptr;  // [na_pad] cores with q = qc + qs/2 (static pass)
+    double4 *cols_static = nullptr;  // [na_pad] cores, CENTRED coordinates, q = qc + qs/2 (static pass)
     float *rowx_f = nullptr;      // unused placeholder (rows are converted in-kernel)
     double centre[3] = {0, 0, 0};
     double inv_grid = 1.0;        // fixed-point grid: 1/grid, grid = 2^-k nm so the box fits +-2^30

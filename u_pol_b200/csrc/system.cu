@@ -46,7 +46,7 @@ __global__ void build_core_columns_kernel(int nsite, int na_pad, const double *_
         const double x = r[3 * i], y = r[3 * i + 1], z = r[3 * i + 2];
         cols[i] = make_double4(x, y, z, qc[i]);
         cols_f[mix_slot[i]] = fix_col(x - cx, y - cy, z - cz, inv_grid, qc[i]);
-        cols_static[i] = make_double4(x, y, z, qc[i] + 0.5 * qs[i]);
+        cols_static[i] = make_double4(x - cx, y - cy, z - cz, qc[i] + 0.5 * qs[i]);
     } else {
         cols[i] = make_double4(kFar, kFar, kFar, 0.0);
         cols_static[i] = make_double4(kFar, kFar, kFar, 0.0);
@@ -301,7 +301,7 @@ int sys_static_part(upol_system *s, cudaStream_t st) {
     a.n_tiles = a.n_tiles_a;
     a.n_split = choose_split(s, a.n_rows, a.n_tiles, fp64_rows_per_block());
     if (a.n_rows > 0) {
-        int rc = launch_pair_fp64(a, true, false, st);
+        int rc = launch_pair_static(a, st);
         if (rc) return rc;
         const int nb = (int)nblk(a.n_rows, kFinBlock);
         finalize_static_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, a.n_split, s->part, a.part_stride,
