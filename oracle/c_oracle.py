@@ -51,3 +51,29 @@ def energy_grad(r_core, d, q_core, q_shell, k, thole_u=None, row_lo=0, row_hi=No
     if rc != 0:
         raise RuntimeError(f"upol_oracle_energy_grad failed: {rc}")
     return e, (g.reshape(nmol, natoms, 3) if want_grad else None)
+
+
+_LIB_LD = os.path.join(_HERE, "libuind_oracle_ld.so")
+_lib_ld = None
+
+
+def uind_long_double(r_core, d, q_core, q_shell, k, thole_u=None):
+    """U_ind from the 80-bit long-double arbiter (oracle/uind_oracle_ld.c); energy only."""
+    global _lib_ld
+    if _lib_ld is None:
+        if not os.path.isfile(_LIB_LD):
+            subprocess.run(["make", "-C", _HERE], check=True)
+        _lib_ld = C.CDLL(_LIB_LD)
+        _lib_ld.upol_oracle_uind_long_double.restype = C.c_double
+        _lib_ld.upol_oracle_uind_long_double.argtypes = [C.c_int64, C.c_int] + [C.c_void_p] * 6
+    r = np.ascontiguousarray(r_core, dtype=np.float64)
+    nmol, natoms = r.shape[0], r.shape[1]
+    n = nmol * natoms
+    dd = np.ascontiguousarray(np.asarray(d, dtype=np.float64).reshape(n, 3))
+    qc, qs, kk = (np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(n)) for a in (q_core, q_shell, k))
+    th = None
+    if thole_u is not None and np.any(np.asarray(thole_u) != 0):
+        th = np.ascontiguousarray(thole_u, dtype=np.float64)
+    return float(_lib_ld.upol_oracle_uind_long_double(n, natoms, r.ctypes.data, dd.ctypes.data, qc.ctypes.data,
+                                                      qs.ctypes.data, kk.ctypes.data,
+                                                      th.ctypes.data if th is not None else None))

@@ -49,3 +49,15 @@ def test_zero_distance_dropped():
     e2, _ = c_oracle.energy_grad(r2, np.concatenate([D, np.zeros((s.nmol, 1, 3))], 1), np.concatenate([s.q_core, z], 1),
                                  np.concatenate([s.q_shell, z], 1), np.concatenate([s.k, z], 1), None)
     assert abs(e2[0] - e[0]) <= 1e-12 * abs(e[0]) + 1e-14 * (abs(e[1]) + abs(e[2]))
+
+
+def test_long_double_arbiter_agrees_with_both_oracles():
+    s = synth.imidazole_box(40, seed=11)
+    D = synth.random_displacements(s, seed=12)
+    e, _ = c_oracle.energy_grad(s.r_core, D, s.q_core, s.q_shell, s.k, s.thole_u, want_grad=False)
+    e_ld = c_oracle.uind_long_double(s.r_core, D, s.q_core, s.q_shell, s.k, s.thole_u)
+    assert e[0] == pytest.approx(e_ld, rel=1e-11)      # fp64 remainder-of-large-sums noise
+    w = synth.water_box(27, seed=13)
+    Dw = synth.random_displacements(w, seed=14)
+    ew, _ = c_oracle.energy_grad(w.r_core, Dw, w.q_core, w.q_shell, w.k, None, want_grad=False)
+    assert ew[0] == pytest.approx(c_oracle.uind_long_double(w.r_core, Dw, w.q_core, w.q_shell, w.k, None), rel=1e-11)

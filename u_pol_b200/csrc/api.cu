@@ -34,13 +34,6 @@ int dev_alloc(T **p, size_t n) {
     return UPOL_OK;
 }
 
-template <typename T>
-int upload(T *dst, const std::vector<T> &src) {
-    if (src.empty()) return UPOL_OK;
-    UPOL_CUDA(cudaMemcpy(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
-    return UPOL_OK;
-}
-
 void free_system(upol_system *s) {
     if (!s) return;
     minimize_free(s);
@@ -63,16 +56,7 @@ void compute_centre(upol_system *s, const double *r_host) {
             lo[c] = std::min(lo[c], r_host[3 * i + c]);
             hi[c] = std::max(hi[c], r_host[3 * i + c]);
         }
-    double half = 0.0;
-    for (int c = 0; c < 3; ++c) {
-        s->centre[c] = s->nsite ? 0.5 * (lo[c] + hi[c]) : 0.0;
-        half = std::max(half, s->nsite ? 0.5 * (hi[c] - lo[c]) : 0.0);
-    }
-    // fixed-point grid of the mixed kernel: 2^-k nm with (half extent + 1 nm of Drude slack)
-    // inside +-2^29, so coordinate differences fit a 32-bit int with room to spare
-    int e = 0;
-    frexp(half + 1.0, &e);                      // half + 1 < 2^e
-    s->inv_grid = ldexp(1.0, 29 - e);
+    set_box(s, lo, hi);
 }
 
 }  // namespace
@@ -208,7 +192,7 @@ int upol_system_create(upol_system **out, int device, int64_t nsite, const doubl
     TRY(dev_alloc(&s->th_ptr, s->nd + 1)); TRY(dev_alloc(&s->th_row, th_row.size())); TRY(dev_alloc(&s->th_u, th_u.size()));
     TRY(dev_alloc(&s->part, part_elems));
     TRY(dev_alloc(&s->dc, 3 * s->nd)); TRY(dev_alloc(&s->gc, 3 * s->nd));
-    s->n_eblock = (int)((std::max<int64_t>(s->nd, nsite) + 127) / 128) + 1;
+    s->n_eblock = (int)((std::max<int64_t>(s->nd, nsite) + 31) / 32) + 1;   // finalize blocks hold 32 rows
     TRY(dev_alloc(&s->eblock, 4 * (size_t)s->n_eblock));
     TRY(dev_alloc(&s->energy, UPOL_E_SIZE)); TRY(dev_alloc(&s->e_static, 2)); TRY(dev_alloc(&s->phi_static, s->nd_pad));
 
@@ -280,8 +264,10 @@ int upol_system_set_positions_dev(upol_system *s, const double *r_core_dev, void
     if (!s || !r_core_dev) return UPOL_ERR_ARG;
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    // the box centre (used only by the fp32 coordinates of mixed mode) is kept from creation
     UPOL_CUDA(cudaMemcpyAsync(s->r, r_core_dev, sizeof(double) * 3 * s->nsite, cudaMemcpyDeviceToDevice, st));
+    // box centre / fixed-point grid follow the new geometry (6 doubles come back to the host)
+    int rc = sys_box_from_device(s, st);
+    if (rc) return rc;
     return sys_upload_positions(s, nullptr, st);
 }
 

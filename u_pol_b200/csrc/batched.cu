@@ -57,19 +57,16 @@ struct WarpMem {
     double *xt;     // [n] trial point
     double *gt;     // [n]
     double *hy;     // [n]
-    double *H;      // [n*n]
-    double *acc;    // [nd*4] phiA, Fx, Fy, Fz per row (+ phiB in a second array)
-    double *accb;   // [nd]
+    double *H;      // [n*n] inverse Hessian
 };
 
-// Field (and optionally potential) at the shells of one system.  Lanes stride over (row, column)
-// tasks; each task's result goes to a fixed slot that one lane owns, so the sum order is fixed.
+// Field (and optionally potential) at the shells of one system: lane = Drude row (nd <= 32), each
+// lane loops over all columns, so the sum order is fixed (deterministic).
 template <bool POT>
 __device__ void eval_system(const BatchTopo &t, const WarpMem &m, const double *xcur, double *gout,
                             double *e_inter, double *e_intra, double *e_self, int lane) {
     const int nd = t.nd, nsite = t.nsite;
-    // rows: lane -> row (nd <= 32).  Each lane owning a row loops over all columns: deterministic,
-    // and for the dimer workload (28 columns, 10 rows) it is ~280 interactions per warp.
+    // dimer workload: 10 rows x 28 columns, ~140 inter-molecular interactions per evaluation
     double ei = 0.0, ea = 0.0, es = 0.0;
     if (lane < nd) {
         const int sa = t.row_site[lane];

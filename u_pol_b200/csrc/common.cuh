@@ -104,7 +104,6 @@ struct upol_system {
     int *exM_lo = nullptr, *exM_len = nullptr;   // [nd_pad] excluded interval of a row in cols_f
     int64_t nm_pad = 0;
     double4 *cols_static = nullptr;  // [na_pad] cores, CENTRED coordinates, q = qc + qs/2 (static pass)
-    float *rowx_f = nullptr;      // unused placeholder (rows are converted in-kernel)
     double centre[3] = {0, 0, 0};
     double inv_grid = 1.0;        // fixed-point grid: 1/grid, grid = 2^-k nm so the box fits +-2^30
     // Thole screened pairs as CSR over Drude rows (ordered pairs)
@@ -147,7 +146,6 @@ struct upol_system {
 namespace upol {
 
 // evaluation pipeline pieces (system.cu / finalize_kernels.cu)
-int sys_prepare_rows(upol_system *s, const double *d_compact, int precision, cudaStream_t st);
 // what one evaluation computes
 struct EvalOpts {
     int precision = UPOL_FP64;     // arithmetic of the FIELD; the potential is always fp64
@@ -167,6 +165,8 @@ int sys_ensure_pinned(upol_system *s, size_t bytes);
 int sys_ensure_hscratch(upol_system *s, size_t elems);
 int choose_split(const upol_system *s, int64_t n_rows, int n_tiles, int rows_per_block);
 int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream_t st);
+void set_box(upol_system *s, const double *lo, const double *hi);
+int sys_box_from_device(upol_system *s, cudaStream_t st);
 int sys_make_sij(const double *rij, const double *u, int u_is_scalar, int64_t n, double *out, cudaStream_t st);
 int sys_coulomb_static(upol_system *s, double *out2, cudaStream_t st);
 const char *last_error_message();

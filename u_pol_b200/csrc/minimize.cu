@@ -97,8 +97,7 @@ dots_kernel(int m, int64_t n, int64_t e0, int64_t e1, const int *__restrict__ ic
     __shared__ double sm[kDotVals][kDotBlock / 32];
     const int l = blockIdx.y;
     double acc[6] = {0, 0, 0, 0, 0, 0};
-    const bool used = l == m || l < ic[I_HCOUNT] || true;   // unused slots hold zeros
-    if (used) {
+    {   // history slots not yet filled hold zeros, so every slot can be summed unconditionally
         const double *a = l < m ? S + (int64_t)l * n : p;
         const double *b = l < m ? Y + (int64_t)l * n : nullptr;
         for (int64_t e = e0 + (int64_t)blockIdx.x * kDotBlock + threadIdx.x; e < e1; e += (int64_t)gridDim.x * kDotBlock) {

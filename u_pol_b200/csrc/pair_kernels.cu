@@ -28,6 +28,18 @@
 
 namespace upol {
 
+// Compensated accumulation (Knuth two-sum) of a tile partial into a (hi, lo) pair.  The row
+// potentials reach ~2e4 e/nm at 100 k Drudes (all core charges positive, all shells negative) while
+// U_ind is their ~1e-6 remainder; adding 128-column tile partials (~10) into such an accumulator
+// costs 2e-12 per add in plain fp64, which over 2000 tiles and 1e5 rows is 1e-10 of U_ind.  Seven
+// adds per TILE per row make that negligible.
+__device__ __forceinline__ void two_sum_acc(double &hi, double &lo, double x) {
+    const double s = hi + x;
+    const double bp = s - hi;
+    lo += (hi - (s - bp)) + (x - bp);
+    hi = s;
+}
+
 // q / r^3 from r^2 without forming 1/r (field-only variant): seed y, e = 1 - x y^2,
 // y^3 (1-e)^(-3/2) = y^3 (1 + 3e/2 + 15e^2/8 + O(e^3)); 7 DP ops, same O(e^3) ~ 1e-20 truncation.
 __device__ __forceinline__ double q_over_r3_f64(double q, double x) {
@@ -61,7 +73,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
     const int row_base = blockIdx.x * (kBlock * ROWS) + tid;
     double sx[ROWS], sy[ROWS], sz[ROWS];
     int loA[ROWS], lenA[ROWS], loB[ROWS], lenB[ROWS];
-    double phA[ROWS], phB[ROWS], fx[ROWS], fy[ROWS], fz[ROWS];
+    double phA[ROWS], phB[ROWS], plA[ROWS], plB[ROWS], fx[ROWS], fy[ROWS], fz[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         const int lr = row_base + r * kBlock;
@@ -70,7 +82,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
         sx[r] = a.rx[i]; sy[r] = a.ry[i]; sz[r] = a.rz[i];
         loA[r] = a.exA_lo[i]; lenA[r] = a.exA_len[i];
         loB[r] = a.exB_lo[i]; lenB[r] = a.exB_len[i];
-        phA[r] = phB[r] = fx[r] = fy[r] = fz[r] = 0.0;
+        phA[r] = phB[r] = plA[r] = plB[r] = fx[r] = fy[r] = fz[r] = 0.0;
     }
 
     const int t0 = (int)(((int64_t)a.n_tiles * blockIdx.y) / a.n_split);
@@ -150,7 +162,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
         if (POT) {
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
-                if (isB) phB[r] += ph[r]; else phA[r] += ph[r];
+                if (isB) two_sum_acc(phB[r], plB[r], ph[r]); else two_sum_acc(phA[r], plA[r], ph[r]);
             }
         }
     }
@@ -161,8 +173,8 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
         const int lr = row_base + r * kBlock;
         if (lr < a.n_rows) {
             if (POT) {
-                out[0 * a.part_stride + lr] = phA[r];
-                out[1 * a.part_stride + lr] = phB[r];
+                out[0 * a.part_stride + lr] = phA[r] + plA[r];
+                out[1 * a.part_stride + lr] = phB[r] + plB[r];
             }
             if (GRAD) {
                 out[2 * a.part_stride + lr] = fx[r];
@@ -208,7 +220,7 @@ __global__ void __launch_bounds__(kBlock) pair_static_kernel(const PairArgs a) {
 
     const int tid = threadIdx.x;
     const int row_base = blockIdx.x * (kBlock * ROWS) + tid;
-    double mx[ROWS], my[ROWS], mz[ROWS], r2i[ROWS], ph[ROWS];
+    double mx[ROWS], my[ROWS], mz[ROWS], r2i[ROWS], ph[ROWS], pl[ROWS];
     int lo[ROWS], len[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
@@ -218,7 +230,7 @@ __global__ void __launch_bounds__(kBlock) pair_static_kernel(const PairArgs a) {
         mx[r] = -2.0 * x; my[r] = -2.0 * y; mz[r] = -2.0 * z;
         r2i[r] = fma(z, z, fma(y, y, x * x));
         lo[r] = a.exA_lo[i]; len[r] = a.exA_len[i];
-        ph[r] = 0.0;
+        ph[r] = pl[r] = 0.0;
     }
     const int t0 = (int)(((int64_t)a.n_tiles * blockIdx.y) / a.n_split);
     const int t1 = (int)(((int64_t)a.n_tiles * (blockIdx.y + 1)) / a.n_split);
@@ -272,13 +284,13 @@ __global__ void __launch_bounds__(kBlock) pair_static_kernel(const PairArgs a) {
             }
         }
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) ph[r] += pt[r];
+        for (int r = 0; r < ROWS; ++r) two_sum_acc(ph[r], pl[r], pt[r]);
     }
     double *out = a.part + (int64_t)blockIdx.y * kPartComps * a.part_stride;
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         const int lr = row_base + r * kBlock;
-        if (lr < a.n_rows) out[lr] = ph[r];
+        if (lr < a.n_rows) out[lr] = ph[r] + pl[r];
     }
 }
 

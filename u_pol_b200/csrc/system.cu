@@ -111,6 +111,37 @@ __device__ __forceinline__ double block_sum(double v, double *sm) {
 }
 
 constexpr int kFinBlock = 128;
+constexpr int kFinRows = 32;      // rows per finalize block: 32 rows x 4 split lanes
+constexpr int kFinLanes = kFinBlock / kFinRows;
+
+// Fold the column-split partials of one row.  A block handles kFinRows rows; thread (lx, ly) sums the
+// splits ly, ly+4, ... of row lx for components [c0, c0+NC) with independent loads in flight, and
+// the four lane sums are combined in fixed order by lane 0 (deterministic).  At small N the split
+// count reaches ~100 and a single thread per row would chain ~500 L2 loads.
+template <int NC>
+__device__ __forceinline__ void fold_splits(const double *__restrict__ part, int64_t stride, int lr, bool live,
+                                            int n_split, int c0, double (*sm)[kFinRows][5], double *out) {
+    const int lx = threadIdx.x % kFinRows, ly = threadIdx.x / kFinRows;
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    if (live) {
+#pragma unroll 4
+        for (int s = ly; s < n_split; s += kFinLanes) {
+            const double *p = part + (int64_t)s * kPartComps * stride + (int64_t)c0 * stride + lr;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc[c] += p[(int64_t)c * stride];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NC; ++c) sm[ly][lx][c] = acc[c];
+    __syncthreads();
+    if (ly == 0) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) out[c] = ((sm[0][lx][c] + sm[1][lx][c]) + sm[2][lx][c]) + sm[3][lx][c];
+    }
+}
 
 // K4b + K2: per Drude row, fold the column-split partials, apply K*qs, add the spring and the
 // intra-molecular Thole pairs, write the gradient row, and emit per-block energy partials.
@@ -124,30 +155,26 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
                      const double *__restrict__ th_u, const double *__restrict__ phi_static,
                      bool with_grad, double *__restrict__ gc, double *__restrict__ eblock) {
     __shared__ double sm[kFinBlock / 32];
+    __shared__ double fold[kFinLanes][kFinRows][5];
     const int gw = gate ? *gate : 0;
     if (gw & kGateDone) return;
     // which field kernel ran decides how many column splits hold force partials
     const int n_split_f = (phase_switch && (gw & kGatePhaseMixed)) ? n_split_mixed : n_split_f64;
-    const int lr = blockIdx.x * kFinBlock + threadIdx.x;
+    const int lr = blockIdx.x * kFinRows + threadIdx.x % kFinRows;
+    const bool live = lr < n_rows;
+    const bool owner = live && threadIdx.x < kFinRows;
+    double pot[2] = {0.0, 0.0}, frc[3] = {0.0, 0.0, 0.0};
+    if (n_split_pot > 0) fold_splits<2>(part, stride, lr, live, n_split_pot, 0, fold, pot);
+    if (with_grad) fold_splits<3>(part, stride, lr, live, n_split_f, 2, fold, frc);
     double e_inter = 0.0, e_intra = 0.0, e_self = 0.0, g2 = 0.0;
-    if (lr < n_rows) {
+    if (owner) {
         const int i = row0 + lr;
-        double pa = 0.0, pb = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
-        for (int s = 0; s < n_split_pot; ++s) {
-            const double *p = part + (int64_t)s * kPartComps * stride + lr;
-            pa += p[0]; pb += p[stride];
-        }
-        if (with_grad) {
-            for (int s = 0; s < n_split_f; ++s) {
-                const double *p = part + (int64_t)s * kPartComps * stride + lr;
-                fx += p[2 * stride]; fy += p[3 * stride]; fz += p[4 * stride];
-            }
-        }
+        const double pa = pot[0], pb = pot[1], fx = frc[0], fy = frc[1], fz = frc[2];
         const double qs = row_qs[i], kk = row_k[i];
         const double dx = dc[3 * i], dy = dc[3 * i + 1], dz = dc[3 * i + 2];
         // (U_coul - U_coul_static) share of the row: static potential removed before the row sum
         const double ps = phi_static ? phi_static[i] : 0.0;
-        e_inter = kCoulomb * qs * ((pa + 0.5 * pb) - ps);
+        e_inter = kCoulomb * qs * ((pa - ps) + 0.5 * pb);
         e_self = 0.5 * kk * (dx * dx + dy * dy + dz * dz);
         double gx = -kCoulomb * qs * fx + kk * dx;
         double gy = -kCoulomb * qs * fy + kk * dy;
@@ -195,11 +222,14 @@ finalize_static_kernel(int n_rows, int row0, int n_split, const double *__restri
                        const double *__restrict__ row_qs, double *__restrict__ phi_static,
                        double *__restrict__ eblock) {
     __shared__ double sm[kFinBlock / 32];
-    const int lr = blockIdx.x * kFinBlock + threadIdx.x;
+    __shared__ double fold[kFinLanes][kFinRows][5];
+    const int lr = blockIdx.x * kFinRows + threadIdx.x % kFinRows;
+    const bool live = lr < n_rows;
+    double pot[1] = {0.0};
+    fold_splits<1>(part, stride, lr, live, n_split, 0, fold, pot);
     double e = 0.0;
-    if (lr < n_rows) {
-        double pa = 0.0;
-        for (int s = 0; s < n_split; ++s) pa += part[(int64_t)s * kPartComps * stride + lr];
+    if (live && threadIdx.x < kFinRows) {
+        const double pa = pot[0];
         // kept PER ROW: the static potential (~1e4 e/nm at 100 k Drudes) is subtracted from the
         // row's core/shell potential before anything is summed over rows, otherwise U_ind
         // (~1e5 kJ/mol) would be the difference of two ~1e11 kJ/mol totals
@@ -303,7 +333,7 @@ int sys_static_part(upol_system *s, cudaStream_t st) {
     if (a.n_rows > 0) {
         int rc = launch_pair_static(a, st);
         if (rc) return rc;
-        const int nb = (int)nblk(a.n_rows, kFinBlock);
+        const int nb = (int)nblk(a.n_rows, kFinRows);
         finalize_static_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, a.n_split, s->part, a.part_stride,
                                                          s->row_qs, s->phi_static, s->eblock);
         reduce_blocks_kernel<<<1, 256, 0, st>>>(nb, 1, s->eblock, s->e_static, 1);
@@ -371,7 +401,7 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
             split_mx = splitmx;
             if (!o.phase_switch) split_f64 = splitmx;   // no gate: the mixed partials are THE field
         }
-        const int nb = (int)nblk(a.n_rows, kFinBlock);
+        const int nb = (int)nblk(a.n_rows, kFinRows);
         finalize_rows_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, split_pot, split_f64, split_mx,
                                                        o.gate, o.phase_switch ? 1 : 0, s->part, a.part_stride,
                                                        s->row_site, s->r, dcmp, s->row_qs, s->row_k,
@@ -437,10 +467,52 @@ int sys_ensure_hscratch(upol_system *s, size_t elems) {
     return UPOL_OK;
 }
 
+// Bounding box of the positions (one block; used by the device-pointer set_positions path).
+__global__ void bbox_kernel(int nsite, const double *__restrict__ r, double *__restrict__ out6) {
+    __shared__ double lo[3][32], hi[3][32];
+    double l[3] = {1e300, 1e300, 1e300}, h[3] = {-1e300, -1e300, -1e300};
+    for (int i = threadIdx.x; i < nsite; i += blockDim.x)
+        for (int c = 0; c < 3; ++c) { const double v = r[3 * i + c]; l[c] = fmin(l[c], v); h[c] = fmax(h[c], v); }
+    for (int c = 0; c < 3; ++c) {
+        for (int o = 16; o > 0; o >>= 1) {
+            l[c] = fmin(l[c], __shfl_down_sync(0xffffffffu, l[c], o));
+            h[c] = fmax(h[c], __shfl_down_sync(0xffffffffu, h[c], o));
+        }
+        if ((threadIdx.x & 31) == 0) { lo[c][threadIdx.x >> 5] = l[c]; hi[c][threadIdx.x >> 5] = h[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int c = 0; c < 3; ++c) {
+            double a = lo[c][0], b = hi[c][0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = fmin(a, lo[c][w]); b = fmax(b, hi[c][w]); }
+            out6[c] = a; out6[3 + c] = b;
+        }
+}
+
+void set_box(upol_system *s, const double *lo, const double *hi) {
+    double half = 0.0;
+    for (int c = 0; c < 3; ++c) {
+        s->centre[c] = s->nsite ? 0.5 * (lo[c] + hi[c]) : 0.0;
+        half = std::max(half, s->nsite ? 0.5 * (hi[c] - lo[c]) : 0.0);
+    }
+    // fixed-point grid of the mixed kernel: 2^-k nm with (half extent + 1 nm of Drude slack)
+    // inside +-2^29, so coordinate differences fit a 32-bit int with room to spare
+    int e = 0;
+    frexp(half + 1.0, &e);                      // half + 1 < 2^e
+    s->inv_grid = ldexp(1.0, 29 - e);
+}
+
+int sys_box_from_device(upol_system *s, cudaStream_t st) {
+    bbox_kernel<<<1, 1024, 0, st>>>((int)s->nsite, s->r, s->eblock);
+    double h[6];
+    UPOL_CUDA(cudaMemcpyAsync(h, s->eblock, sizeof(h), cudaMemcpyDeviceToHost, st));
+    UPOL_CUDA(cudaStreamSynchronize(st));
+    set_box(s, h, h + 3);
+    return UPOL_OK;
+}
+
 int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream_t st) {
-    // r already in s->r (device).  Box centre from the host copy is not available for the
-    // device-pointer path, so the centre is computed on the device-free side only when the
-    // host copy is given; here we (re)build the columns with the current centre.
+    // r is already in s->r (device); (re)build the d-independent columns with the current box
     (void)r_dev_or_null;
     build_core_columns_kernel<<<nblk(std::max(s->na_pad, s->nm_pad), 256), 256, 0, st>>>(
         (int)s->nsite, (int)s->na_pad, s->r, s->qc, s->qs, s->centre[0], s->centre[1], s->centre[2], s->inv_grid,
@@ -481,11 +553,14 @@ finalize_sites_kernel(int nsite, int n_split, const double *__restrict__ part, i
                       const double *__restrict__ qc, const double *__restrict__ qs, int total,
                       double *__restrict__ eblock) {
     __shared__ double sm[kFinBlock / 32];
-    const int i = blockIdx.x * kFinBlock + threadIdx.x;
+    __shared__ double fold[kFinLanes][kFinRows][5];
+    const int i = blockIdx.x * kFinRows + threadIdx.x % kFinRows;
+    const bool live = i < nsite;
+    double pot[1] = {0.0};
+    fold_splits<1>(part, stride, i, live, n_split, 0, fold, pot);
     double e = 0.0;
-    if (i < nsite) {
-        double pa = 0.0;
-        for (int s = 0; s < n_split; ++s) pa += part[(int64_t)s * kPartComps * stride + i];
+    if (live && threadIdx.x < kFinRows) {
+        const double pa = pot[0];
         e = 0.5 * kCoulomb * (total ? qc[i] + qs[i] : qc[i]) * pa;
     }
     const double s0 = block_sum<kFinBlock>(e, sm);
@@ -502,7 +577,7 @@ int sys_coulomb_static(upol_system *s, double *out2, cudaStream_t st) {
     const int64_t rb = (n + kRowTile - 1) / kRowTile;
     int split = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (148 * 8 + rb - 1) / rb));
     const int64_t stride = part_stride_for(n);
-    const int nb = (int)nblk(n, kFinBlock);
+    const int nb = (int)nblk(n, kFinRows);
     UPOL_CUDA(cudaMalloc((void **)&rows, sizeof(double) * 3 * n));
     UPOL_CUDA(cudaMalloc((void **)&ex, sizeof(int) * 4 * n));
     UPOL_CUDA(cudaMalloc((void **)&cols, sizeof(double4) * s->na_pad));
