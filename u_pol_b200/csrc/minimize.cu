@@ -4,9 +4,14 @@
 // jaxopt's dense BFGS keeps a (3N)^2 inverse Hessian and an energy-based zoom line search; both
 // stop working at scale (H is 2.3 TB at 100 k Drudes, and near the
 // minimum dE ~ g^2/2k is below the round-off of an N^2-term fp64 sum).  This minimiser is
-//   * limited-memory BFGS in the compact (Byrd-Nocedal-Schnabel) form with H0 = gamma*diag(1/k)
-//     - U_ind is near-quadratic with a spring-dominated Hessian, so diag(1/k) is a good
-//     preconditioner and the unit step is almost always accepted (one gradient per iteration);
+//   * limited-memory BFGS in the compact (Byrd-Nocedal-Schnabel) form with H0 = gamma*P, where P
+//     is the inverse of the MOLECULE-BLOCK Hessian at d = 0: springs on the diagonal and the
+//     Thole-damped dipole-dipole tensors -K qs_a qs_b grad grad g(R_ab) between the screened pairs
+//     of a molecule (the strongest couplings in the system; their block has condition number ~4
+//     for the imidazole force field).  Blocks are built and inverted on the device, one thread
+//     per molecule.  Against P = diag(1/k) this takes 12 instead of 20 iterations on the liquid
+//     boxes.  U_ind is near-quadratic, so the unit step is almost always accepted (one gradient
+//     evaluation per iteration);
 //   * a line search driven by directional derivatives only: accept when
 //     0.9 phi'(0) <= phi'(a) <= -0.8 phi'(0) (approximate Wolfe), otherwise a safeguarded
 //     secant step on phi'; energies are never compared;
@@ -21,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -41,8 +47,14 @@ enum { D_ALPHA = 0, D_ALPHA_PREV, D_PHI0, D_ALO, D_DLO, D_AHI, D_DHI, D_GAMMA, D
 struct MinWs {
     int m = 0;
     int64_t n = 0;             // 3 * nd
-    double *x0 = nullptr, *g0 = nullptr, *p = nullptr, *g = nullptr, *pinv = nullptr;
-    double *S = nullptr, *Y = nullptr;       // [m][n]
+    double *x0 = nullptr, *g0 = nullptr, *p = nullptr, *g = nullptr;
+    double *Pg = nullptr, *Py = nullptr;     // [n] preconditioned gradient / gradient change
+    double *S = nullptr, *Y = nullptr;       // [m][n] history: s_l and P y_l (y_l itself is never needed)
+    double *blk = nullptr;                   // inverse molecule blocks, (3 nrow_m)^2 doubles each
+    int64_t *blk_off = nullptr;              // [nmol] offset of a molecule's block
+    int *mol_row0 = nullptr, *mol_nrow = nullptr, *row_mol = nullptr;
+    int64_t blk_elems = 0;
+    int64_t nmol = 0;
     double *partial = nullptr;               // [nblocks][(m+1)*kDotVals]
     double *pack = nullptr;                  // [(m+1)*kDotVals]
     double *sc = nullptr;                    // [D_SIZE]
@@ -58,8 +70,8 @@ struct MinWs {
 
 void ws_free(MinWs *w) {
     if (!w) return;
-    void *ptrs[] = {w->x0, w->g0, w->p, w->g, w->pinv, w->S, w->Y, w->partial, w->pack, w->sc, w->ic,
-                    w->coef, w->RS, w->YY, w->e_final};
+    void *ptrs[] = {w->x0, w->g0, w->p, w->g, w->Pg, w->Py, w->S, w->Y, w->partial, w->pack, w->sc, w->ic,
+                    w->coef, w->RS, w->YY, w->e_final, w->blk, w->blk_off, w->mol_row0, w->mol_nrow, w->row_mol};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (w->h_ic) cudaFreeHost(w->h_ic);
     if (w->h_sc) cudaFreeHost(w->h_sc);
@@ -67,11 +79,100 @@ void ws_free(MinWs *w) {
     delete w;
 }
 
-__global__ void init_pinv_kernel(int64_t n, const double *__restrict__ row_k, double *__restrict__ pinv) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    const double k = row_k[e / 3];
-    pinv[e] = k > 0.0 ? 1.0 / k : 1.0;
+// Second derivative tensor of g(x) = S(u|x|)/|x| (make_Sij, polarization.py:27-31):
+//   grad g = c(r) x,  c = (S' r - S)/r^3;   grad grad g = c I + (c'/r) x x^T,
+//   c' = S''/r^2 - 3 (S' r - S)/r^4,  S' = u(1+ur)e^{-ur}/2,  S'' = -u^3 r e^{-ur}/2.
+__device__ void thole_hessian(double x, double y, double z, double u, double G[3][3]) {
+    const double r2 = x * x + y * y + z * z;
+    if (r2 == 0.0) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) G[i][j] = 0.0; return; }
+    const double r = sqrt(r2), ex = exp(-u * r);
+    const double S = 1.0 - (1.0 + 0.5 * r * u) * ex, Sp = 0.5 * u * (1.0 + u * r) * ex, Spp = -0.5 * u * u * u * r * ex;
+    const double t = Sp * r - S;
+    const double c = t / (r2 * r), cpr = (Spp / r2 - 3.0 * t / (r2 * r2)) / r;
+    const double v[3] = {x, y, z};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) G[i][j] = (i == j ? c : 0.0) + cpr * v[i] * v[j];
+}
+
+// One thread per molecule: block Hessian of (springs + Thole intra pairs) at d = 0, inverted in
+// place (Gauss-Jordan on an SPD matrix).  H_aa = k_a I,  H_ab = -K qs_a qs_b grad grad g(R_ab)
+// (only the g(C) term of polarization.py:94-99 couples d_a and d_b; the others cancel at d = 0).
+// A non-positive pivot (would mean an intra-molecular polarisation catastrophe) falls back to
+// the diagonal 1/k.
+__global__ void build_blocks_kernel(int mol_lo, int mol_hi, const int *__restrict__ mol_row0,
+                                    const int *__restrict__ mol_nrow, const int64_t *__restrict__ blk_off,
+                                    const int *__restrict__ row_site, const double *__restrict__ r,
+                                    const double *__restrict__ row_qs, const double *__restrict__ row_k,
+                                    const int *__restrict__ th_ptr, const int *__restrict__ th_row,
+                                    const double *__restrict__ th_u, double *__restrict__ blk) {
+    const int m = mol_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= mol_hi) return;
+    const int r0 = mol_row0[m], nr = mol_nrow[m], nb = 3 * nr;
+    if (nr == 0) return;
+    double *A = blk + blk_off[m];
+    for (int i = 0; i < nb * nb; ++i) A[i] = 0.0;
+    bool coupled = false;
+    for (int a = 0; a < nr; ++a) {
+        const double k = row_k[r0 + a];
+        for (int c = 0; c < 3; ++c) A[(3 * a + c) * nb + 3 * a + c] = k > 0.0 ? k : 1.0;
+        const int sa = row_site[r0 + a];
+        for (int q = th_ptr[r0 + a]; q < th_ptr[r0 + a + 1]; ++q) {
+            const int b = th_row[q] - r0, sb = row_site[th_row[q]];
+            double G[3][3];
+            thole_hessian(r[3 * sb] - r[3 * sa], r[3 * sb + 1] - r[3 * sa + 1], r[3 * sb + 2] - r[3 * sa + 2], th_u[q], G);
+            const double qq = -kCoulomb * row_qs[r0 + a] * row_qs[r0 + b];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) A[(3 * a + i) * nb + 3 * b + j] = qq * G[i][j];
+            coupled = true;
+        }
+    }
+    bool ok = true;
+    if (coupled) {
+        for (int c = 0; c < nb && ok; ++c) {          // in-place Gauss-Jordan inverse
+            const double piv = A[c * nb + c];
+            if (!(piv > 0.0)) { ok = false; break; }
+            const double ip = 1.0 / piv;
+            A[c * nb + c] = 1.0;
+            for (int j = 0; j < nb; ++j) A[c * nb + j] *= ip;
+            for (int i = 0; i < nb; ++i) {
+                if (i == c) continue;
+                const double f = A[i * nb + c];
+                if (f == 0.0) continue;
+                A[i * nb + c] = 0.0;
+                for (int j = 0; j < nb; ++j) A[i * nb + j] -= f * A[c * nb + j];
+            }
+        }
+    }
+    if (!coupled || !ok) {
+        for (int i = 0; i < nb * nb; ++i) A[i] = 0.0;
+        for (int a = 0; a < nr; ++a) {
+            const double k = row_k[r0 + a];
+            for (int c = 0; c < 3; ++c) A[(3 * a + c) * nb + 3 * a + c] = k > 0.0 ? 1.0 / k : 1.0;
+        }
+    }
+}
+
+// Pg = P g and Py = P (g - g0) over the local slice (block mat-vec, blocks are tiny).
+__global__ void __launch_bounds__(256)
+precond_apply_kernel(int64_t e0, int64_t e1, const int *__restrict__ ic, const int *__restrict__ row_mol,
+                     const int *__restrict__ mol_row0, const int *__restrict__ mol_nrow,
+                     const int64_t *__restrict__ blk_off, const double *__restrict__ blk,
+                     const double *__restrict__ g, const double *__restrict__ g0,
+                     double *__restrict__ Pg, double *__restrict__ Py) {
+    if (ic[I_GATE] & kGateDone) return;
+    const int64_t e = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= e1) return;
+    const int m = row_mol[e / 3];
+    const int64_t b0 = 3 * (int64_t)mol_row0[m];
+    const int nb = 3 * mol_nrow[m];
+    const double *row = blk + blk_off[m] + (e - b0) * nb;
+    double a = 0.0, b = 0.0;
+    for (int j = 0; j < nb; ++j) {
+        const double gj = g[b0 + j];
+        a += row[j] * gj;
+        b += row[j] * (gj - g0[b0 + j]);
+    }
+    Pg[e] = a; Py[e] = b;
 }
 
 __global__ void init_state_kernel(int *ic, double *sc, double tol, int phase_bits) {
@@ -91,8 +192,8 @@ __global__ void init_state_kernel(int *ic, double *sc, double tol, int phase_bit
 __global__ void __launch_bounds__(kDotBlock)
 dots_kernel(int m, int64_t n, int64_t e0, int64_t e1, const int *__restrict__ ic,
             const double *__restrict__ S, const double *__restrict__ Y, const double *__restrict__ g,
-            const double *__restrict__ g0, const double *__restrict__ p, const double *__restrict__ pinv,
-            double *__restrict__ partial) {
+            const double *__restrict__ g0, const double *__restrict__ p, const double *__restrict__ Pg,
+            const double *__restrict__ Py, double *__restrict__ partial) {
     if (ic[I_GATE] & kGateDone) return;
     __shared__ double sm[kDotVals][kDotBlock / 32];
     const int l = blockIdx.y;
@@ -101,14 +202,14 @@ dots_kernel(int m, int64_t n, int64_t e0, int64_t e1, const int *__restrict__ ic
         const double *a = l < m ? S + (int64_t)l * n : p;
         const double *b = l < m ? Y + (int64_t)l * n : nullptr;
         for (int64_t e = e0 + (int64_t)blockIdx.x * kDotBlock + threadIdx.x; e < e1; e += (int64_t)gridDim.x * kDotBlock) {
-            const double ge = g[e], ye = ge - g0[e], pe = pinv[e];
+            const double ge = g[e], ye = ge - g0[e];
             if (l < m) {
-                const double se = a[e], yl = b[e] * pe;
+                const double se = a[e], yl = b[e];          // b holds P y_l (P symmetric)
                 acc[0] += se * ye; acc[1] += yl * ye; acc[2] += se * ge; acc[3] += yl * ge;
             } else {
-                const double ae = a[e];
-                acc[0] += ae * ye; acc[1] += ye * pe * ye; acc[2] += ae * ge; acc[3] += ye * pe * ge;
-                acc[4] += ge * ge; acc[5] += ge * pe * ge;
+                const double ae = a[e], pye = Py[e];
+                acc[0] += ae * ye; acc[1] += ye * pye; acc[2] += ae * ge; acc[3] += pye * ge;
+                acc[4] += ge * ge; acc[5] += ge * Pg[e];
             }
         }
     }
@@ -296,22 +397,23 @@ __global__ void __launch_bounds__(256)
 update_kernel(int m, int64_t n, int64_t e0, int64_t e1, const int *__restrict__ ic, const double *__restrict__ sc,
               const double *__restrict__ coef, double *__restrict__ S, double *__restrict__ Y,
               double *__restrict__ x, double *__restrict__ x0, const double *__restrict__ g,
-              double *__restrict__ g0, double *__restrict__ p, const double *__restrict__ pinv) {
+              double *__restrict__ g0, double *__restrict__ p, const double *__restrict__ Pg,
+              const double *__restrict__ Py) {
     if (ic[I_GATE] & kGateDone) return;
     const int64_t e = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= e1) return;
     if (ic[I_ACCEPT]) {
-        const double ge = g[e], pe = pinv[e];
+        const double ge = g[e];
         if (ic[I_PUSHED]) {
             const int ns = ic[I_NEWSLOT];
             S[(int64_t)ns * n + e] = sc[D_ALPHA_PREV] * p[e];
-            Y[(int64_t)ns * n + e] = ge - g0[e];
+            Y[(int64_t)ns * n + e] = Py[e];                 // P y_new
         }
         const double gamma = sc[D_GAMMA];
-        double pn = -gamma * pe * ge;
+        double pn = -gamma * Pg[e];
         for (int l = 0; l < m; ++l) {
             const double a = coef[l], b = coef[kMaxHist + l];
-            if (a != 0.0 || b != 0.0) pn += -a * S[(int64_t)l * n + e] + gamma * pe * b * Y[(int64_t)l * n + e];
+            if (a != 0.0 || b != 0.0) pn += -a * S[(int64_t)l * n + e] + gamma * b * Y[(int64_t)l * n + e];
         }
         const double xe = x[e];
         x0[e] = xe; g0[e] = ge; p[e] = pn;
@@ -337,7 +439,7 @@ static int ws_ensure(upol_system *s, int m, MinWs **out) {
     const int64_t nn = std::max<int64_t>(n, 1);
     w->nblocks = (int)std::min<int64_t>(148 * 2, (nn + kDotBlock - 1) / kDotBlock);
     auto A = [&](double **p, size_t cnt) { return cudaMalloc((void **)p, sizeof(double) * std::max<size_t>(cnt, 1)) == cudaSuccess; };
-    bool ok = A(&w->x0, nn) && A(&w->g0, nn) && A(&w->p, nn) && A(&w->g, nn) && A(&w->pinv, nn) &&
+    bool ok = A(&w->x0, nn) && A(&w->g0, nn) && A(&w->p, nn) && A(&w->g, nn) && A(&w->Pg, nn) && A(&w->Py, nn) &&
               A(&w->S, (size_t)std::max(m, 1) * nn) && A(&w->Y, (size_t)std::max(m, 1) * nn) &&
               A(&w->partial, (size_t)w->nblocks * (m + 1) * kDotVals) && A(&w->pack, (size_t)(m + 1) * kDotVals) &&
               A(&w->sc, D_SIZE) && A(&w->coef, 2 * kMaxHist) && A(&w->RS, (size_t)std::max(m * m, 1)) &&
@@ -346,6 +448,34 @@ static int ws_ensure(upol_system *s, int m, MinWs **out) {
     ok = ok && cudaMallocHost((void **)&w->h_ic, sizeof(int) * I_SIZE * 2) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&w->h_sc, sizeof(double) * D_SIZE * 2) == cudaSuccess;
     for (auto &e : w->ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    // molecule-block tables of the preconditioner
+    {
+        w->nmol = s->nmol;
+        std::vector<int64_t> off(std::max<int64_t>(s->nmol, 1), 0);
+        std::vector<int> rmol(std::max<int64_t>(s->nd, 1), 0);
+        int64_t tot = 0;
+        int max_rows = 0;
+        for (int64_t mm = 0; mm < s->nmol; ++mm) {
+            off[mm] = tot;
+            const int nr = s->h_mol_nrow[mm];
+            max_rows = std::max(max_rows, nr);
+            tot += (int64_t)9 * nr * nr;
+            for (int a = 0; a < nr; ++a) rmol[s->h_mol_row0[mm] + a] = (int)mm;
+        }
+        w->blk_elems = std::max<int64_t>(tot, 1);
+        ok = ok && A(&w->blk, (size_t)w->blk_elems);
+        ok = ok && cudaMalloc((void **)&w->blk_off, sizeof(int64_t) * off.size()) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&w->mol_row0, sizeof(int) * off.size()) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&w->mol_nrow, sizeof(int) * off.size()) == cudaSuccess;
+        ok = ok && cudaMalloc((void **)&w->row_mol, sizeof(int) * rmol.size()) == cudaSuccess;
+        if (ok && s->nmol > 0) {
+            ok = ok && cudaMemcpy(w->blk_off, off.data(), sizeof(int64_t) * s->nmol, cudaMemcpyHostToDevice) == cudaSuccess;
+            ok = ok && cudaMemcpy(w->mol_row0, s->h_mol_row0.data(), sizeof(int) * s->nmol, cudaMemcpyHostToDevice) == cudaSuccess;
+            ok = ok && cudaMemcpy(w->mol_nrow, s->h_mol_nrow.data(), sizeof(int) * s->nmol, cudaMemcpyHostToDevice) == cudaSuccess;
+            ok = ok && cudaMemcpy(w->row_mol, rmol.data(), sizeof(int) * rmol.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+        (void)max_rows;
+    }
     if (!ok) { set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__); ws_free(w); return UPOL_ERR_ALLOC; }
     s->min_ws = w;
     *out = w;
@@ -366,7 +496,10 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
     const int64_t nloc = std::max<int64_t>(e1 - e0, 0);
     const unsigned ublocks = (unsigned)std::max<int64_t>(1, (nloc + 255) / 256);
 
-    if (n > 0) init_pinv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, s->row_k, w->pinv);
+    if (s->mol_hi > s->mol_lo)      // preconditioner blocks of this rank's molecules, current geometry
+        build_blocks_kernel<<<(unsigned)((s->mol_hi - s->mol_lo + 63) / 64), 64, 0, st>>>(
+            (int)s->mol_lo, (int)s->mol_hi, w->mol_row0, w->mol_nrow, w->blk_off, s->row_site, s->r, s->row_qs,
+            s->row_k, s->th_ptr, s->th_row, s->th_u, w->blk);
     init_state_kernel<<<1, 1, 0, st>>>(w->ic, w->sc, o->tol, mixed ? kGatePhaseMixed : kGatePhase64);
     UPOL_CUDA(cudaMemsetAsync(w->S, 0, sizeof(double) * (size_t)std::max(m, 1) * std::max<int64_t>(n, 1), st));
     UPOL_CUDA(cudaMemsetAsync(w->Y, 0, sizeof(double) * (size_t)std::max(m, 1) * std::max<int64_t>(n, 1), st));
@@ -387,11 +520,13 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
         int r = sys_eval_compact(s, x, eo, s->energy, w->g, st);
         if (r) return r;
         dim3 dg((unsigned)w->nblocks, (unsigned)(m + 1));
-        dots_kernel<<<dg, kDotBlock, 0, st>>>(m, n, e0, e1, w->ic, w->S, w->Y, w->g, w->g0, w->p, w->pinv, w->partial);
+        precond_apply_kernel<<<ublocks, 256, 0, st>>>(e0, e1, w->ic, w->row_mol, w->mol_row0, w->mol_nrow, w->blk_off,
+                                                      w->blk, w->g, w->g0, w->Pg, w->Py);
+        dots_kernel<<<dg, kDotBlock, 0, st>>>(m, n, e0, e1, w->ic, w->S, w->Y, w->g, w->g0, w->p, w->Pg, w->Py, w->partial);
         dots_reduce_kernel<<<((m + 1) * kDotVals + 127) / 128, 128, 0, st>>>(m, w->nblocks, w->ic, w->partial, w->pack);
         if (s->nranks > 1) { r = comm_allreduce_sum(s, w->pack, (int64_t)(m + 1) * kDotVals, st); if (r) return r; }
         control_kernel<<<1, 1, 0, st>>>(m, o->maxiter, mixed ? 1 : 0, w->ic, w->sc, w->pack, w->RS, w->YY, w->coef);
-        update_kernel<<<ublocks, 256, 0, st>>>(m, n, e0, e1, w->ic, w->sc, w->coef, w->S, w->Y, x, w->x0, w->g, w->g0, w->p, w->pinv);
+        update_kernel<<<ublocks, 256, 0, st>>>(m, n, e0, e1, w->ic, w->sc, w->coef, w->S, w->Y, x, w->x0, w->g, w->g0, w->p, w->Pg, w->Py);
         if (s->nranks > 1) { r = comm_allgather_rows(s, x, st); if (r) return r; }
         UPOL_CUDA(cudaGetLastError());
         return UPOL_OK;
