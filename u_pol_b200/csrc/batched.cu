@@ -6,8 +6,8 @@
 // All systems share one topology (charges, spring constants, molecule ids, screened pairs) and
 // differ in core positions.  Per system: the shells' field from the other molecules' charges
 // (same formulas as pair_kernels.cu), Thole intra pairs and springs (as finalize_rows_kernel),
-// dense inverse-Hessian BFGS with H0 = diag(1/k) (the reference's jaxopt.BFGS uses H0 = I,
-// polarization.py:178), the same derivative-only line search and ||grad||_2 <= tol stop rule as
+// dense inverse-Hessian BFGS started from the inverse intra-molecular block Hessian (springs +
+// Thole dipole tensors; the reference's jaxopt.BFGS uses H0 = I, polarization.py:178), the same derivative-only line search and ||grad||_2 <= tol stop rule as
 // minimize.cu.  Everything of a system lives in the shared memory slice of its warp; no global
 // traffic besides reading r and writing d, the energy vector and the iteration count.
 #include <algorithm>
@@ -36,6 +36,19 @@ struct BatchTopo {          // device pointers, shared by all systems
 __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// grad grad g (see minimize.cu::thole_hessian)
+__device__ void thole_hess(double x, double y, double z, double u, double G[3][3]) {
+    const double r2 = x * x + y * y + z * z;
+    if (r2 == 0.0) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) G[i][j] = 0.0; return; }
+    const double r = sqrt(r2), ex = exp(-u * r);
+    const double S = 1.0 - (1.0 + 0.5 * r * u) * ex, Sp = 0.5 * u * (1.0 + u * r) * ex, Spp = -0.5 * u * u * u * r * ex;
+    const double t = Sp * r - S;
+    const double c = t / (r2 * r), cpr = (Spp / r2 - 3.0 * t / (r2 * r2)) / r;
+    const double v[3] = {x, y, z};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) G[i][j] = (i == j ? c : 0.0) + cpr * v[i] * v[j];
 }
 
 __device__ __forceinline__ void thole_gc(double x, double y, double z, double u, double &g, double &c) {
@@ -160,10 +173,46 @@ __global__ void batched_bfgs_kernel(BatchTopo t, const double *__restrict__ site
     double *dg = d_all + sys * 3 * nsite;
     for (int i = lane; i < 3 * nsite; i += 32) m.r[i] = rg[i];
     for (int i = lane; i < n; i += 32) m.x[i] = dg[3 * t.row_site[i / 3] + i % 3];
+    // H0 = inverse of the intra-molecular block Hessian at d = 0 (springs + Thole dipole tensors, as
+    // minimize.cu::build_blocks_kernel); inverted in place by the warp (Gauss-Jordan, SPD).
     for (int i = lane; i < n * n; i += 32) m.H[i] = 0.0;
     __syncwarp();
-    for (int i = lane; i < n; i += 32) { const double k = t.row_k[i / 3]; m.H[i * n + i] = k > 0.0 ? 1.0 / k : 1.0; }
+    if (lane < nd) {
+        const int a = lane, sa = t.row_site[a];
+        const double k = t.row_k[a];
+        for (int c = 0; c < 3; ++c) m.H[(3 * a + c) * n + 3 * a + c] = k > 0.0 ? k : 1.0;
+        for (int q = t.th_ptr[a]; q < t.th_ptr[a + 1]; ++q) {
+            const int b = t.th_row[q], sb = t.row_site[b];
+            double G[3][3];
+            thole_hess(m.r[3 * sb] - m.r[3 * sa], m.r[3 * sb + 1] - m.r[3 * sa + 1], m.r[3 * sb + 2] - m.r[3 * sa + 2], t.th_u[q], G);
+            const double qq = -kCoulomb * t.row_qs[a] * t.row_qs[b];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) m.H[(3 * a + i) * n + 3 * b + j] = qq * G[i][j];
+        }
+    }
     __syncwarp();
+    bool spd = true;
+    for (int c = 0; c < n; ++c) {
+        const double piv = m.H[c * n + c];
+        if (!(piv > 0.0)) { spd = false; break; }          // warp-uniform (shared memory value)
+        const double ip = 1.0 / piv;
+        __syncwarp();
+        for (int j = lane; j < n; j += 32) m.H[c * n + j] = (j == c ? 1.0 : m.H[c * n + j]) * ip;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            if (i == c) continue;
+            const double f = m.H[i * n + c];
+            if (f == 0.0) continue;
+            for (int j = 0; j < n; ++j) m.H[i * n + j] = (j == c ? 0.0 : m.H[i * n + j]) - f * m.H[c * n + j];
+        }
+        __syncwarp();
+    }
+    if (!spd) {
+        for (int i = lane; i < n * n; i += 32) m.H[i] = 0.0;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) { const double k = t.row_k[i / 3]; m.H[i * n + i] = k > 0.0 ? 1.0 / k : 1.0; }
+        __syncwarp();
+    }
 
     double e0, e1, e2;
     eval_system<false>(t, m, m.x, m.g, &e0, &e1, &e2, lane);
