@@ -124,6 +124,13 @@ int upol_uind_energy_grad_host(upol_system *sys, const double *d, int precision,
                                double *energy, double *grad);
 
 /*
+ * dUind/dr_core at fixed displacements, dudr[nsite*3] (kJ mol^-1 nm^-1); the force on core i is
+ * -dudr[i].  NEW relative to the reference (SURVEY 8f "next" #3): U_pol has no such function; it
+ * is what an MD driver needs to move the cores on the U_ind surface.  fp64; single rank.
+ */
+int upol_uind_core_gradient_dev(upol_system *sys, const double *d, double *dudr, void *stream);
+
+/*
  * d-independent Coulomb sums needed to rebuild the reference's separate Ucoul / Ucoul_static
  * values (polarization.py:50-61 and the qc*qc term of :82-86):
  *   out[0] = K sum_{i<j, inter} qc_i qc_j / R_ij

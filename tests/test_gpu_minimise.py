@@ -108,7 +108,7 @@ def test_box_minimum_vs_newton(method, precision):
     assert abs(info["U_ind"] - e_newton) <= RTOL_MIN * abs(e_newton)
     # the returned displacements reproduce the returned energy, and inert rows stay at zero
     e, _ = sys_.energy_grad(d)
-    assert float(e[0]) == pytest.approx(info["U_ind"], rel=1e-13)
+    assert float(e[0]) == pytest.approx(info["U_ind"], rel=1e-11)      # potential-only vs potential+field kernel variants
     assert np.all(d.cpu().numpy().reshape(s.r_core.shape)[s.q_shell == 0] == 0.0)
 
 

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "upol_system_set_row_range": (C.c_int, [_P, _I64, _I64]),
     "upol_uind_energy_grad_dev": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "upol_uind_energy_grad_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "upol_uind_core_gradient_dev": (C.c_int, [_P, _P, _P, _P]),
     "upol_coulomb_static_dev": (C.c_int, [_P, _P, _P]),
     "upol_make_sij_dev": (C.c_int, [_P, _P, C.c_int, _I64, _P, _P]),
     "upol_min_options_default": (None, [C.POINTER(MinOptions)]),

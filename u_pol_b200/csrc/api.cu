@@ -41,7 +41,8 @@ void free_system(upol_system *s) {
     void *ptrs[] = {s->r, s->qc, s->qs, s->k, s->row_site, s->row_qs, s->row_k, s->exA_lo, s->exA_len,
                     s->exB_lo, s->exB_len, s->rowx, s->rowy, s->rowz, s->srowx, s->srowy, s->srowz,
                     s->cols, s->cols_f, s->mix_slot, s->exM_lo, s->exM_len, s->cols_static, s->th_ptr, s->th_row, s->th_u, s->part, s->dc,
-                    s->gc, s->eblock, s->energy, s->e_static, s->phi_static};
+                    s->gc, s->eblock, s->energy, s->e_static, s->phi_static, s->site_row,
+                    s->cols_dcore, s->site_x, s->exS_lo, s->cf_tmp};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (s->pin) cudaFreeHost(s->pin);
     if (s->hscratch) cudaFree(s->hscratch);
@@ -174,13 +175,14 @@ int upol_system_create(upol_system **out, int device, int64_t nsite, const doubl
     // with rb row blocks of <= 512 rows, S*stride <= (1184/rb + 1)(512 rb + 511), which the
     // allocation below covers for the full system and for every row shard of it.
     s->max_split = 256;
-    const size_t part_elems = (size_t)kPartComps * ((size_t)148 * 64 * 1024 + (size_t)s->nd_pad + 1024);
+    const size_t part_elems = (size_t)kPartComps * ((size_t)148 * 64 * 1024 + (size_t)std::max<int64_t>(s->nd_pad, round_up(nsite, 512)) + 1024);
 
     int rc = UPOL_OK;
 #define TRY(x) do { rc = (x); if (rc) { free_system(s); return rc; } } while (0)
     TRY(dev_alloc(&s->r, 3 * nsite));
     TRY(dev_alloc(&s->qc, nsite)); TRY(dev_alloc(&s->qs, nsite)); TRY(dev_alloc(&s->k, nsite));
     TRY(dev_alloc(&s->row_site, s->nd)); TRY(dev_alloc(&s->row_qs, s->nd)); TRY(dev_alloc(&s->row_k, s->nd));
+    TRY(dev_alloc(&s->site_row, nsite));
     TRY(dev_alloc(&s->exA_lo, s->nd_pad)); TRY(dev_alloc(&s->exA_len, s->nd_pad));
     TRY(dev_alloc(&s->exB_lo, s->nd_pad)); TRY(dev_alloc(&s->exB_len, s->nd_pad));
     TRY(dev_alloc(&s->rowx, s->nd_pad)); TRY(dev_alloc(&s->rowy, s->nd_pad)); TRY(dev_alloc(&s->rowz, s->nd_pad));
@@ -206,6 +208,7 @@ int upol_system_create(upol_system **out, int device, int64_t nsite, const doubl
         cp(s->qs, q_shell, sizeof(double) * nsite);
         cp(s->k, k, sizeof(double) * nsite);
         cp(s->row_site, s->h_drude_site.data(), sizeof(int32_t) * s->nd);
+        cp(s->site_row, s->h_site_row.data(), sizeof(int32_t) * nsite);
         cp(s->row_qs, row_qs.data(), sizeof(double) * s->nd);
         cp(s->row_k, row_k.data(), sizeof(double) * s->nd);
         cp(s->exA_lo, exA_lo.data(), sizeof(int32_t) * s->nd_pad);
@@ -364,6 +367,15 @@ int upol_system_kernel_time(upol_system *s, double *ms_total, int32_t *launches)
     *launches = s->tev_used / 2;
     s->tev_used = 0;
     return UPOL_OK;
+}
+
+int upol_uind_core_gradient_dev(upol_system *s, const double *d, double *dudr, void *stream) {
+    if (!s || !d || !dudr) return UPOL_ERR_ARG;
+    DeviceGuard guard(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = sys_gather_d(s, d, s->dc, st);
+    if (rc) return rc;
+    return sys_core_forces(s, s->dc, dudr, st);
 }
 
 int upol_coulomb_static_dev(upol_system *s, double *out2, void *stream) {

@@ -24,7 +24,7 @@ constexpr int kBlock = 128;
 constexpr int kTileCols = 128;
 constexpr int kRowsPerThread = 2;
 constexpr int kRowTile = kBlock * kRowsPerThread;
-constexpr int kPartComps = 5;   // phi_core, phi_shell, Fx, Fy, Fz
+constexpr int kPartComps = 6;   // phi_core, phi_shell, Fx, Fy, Fz (+1: the core-force pass stores two fields)
 
 #define UPOL_CUDA(expr)                                   \
     do {                                                  \
@@ -49,6 +49,7 @@ struct PairArgs {
     const int *exB_lo, *exB_len;  // excluded column interval inside section B (per row, already offset)
     // columns: concatenated, each section padded to a multiple of kTileCols
     const void *cols;           // double4* (fp64): x, y, z, q;  int4* (mixed): fixed-point x, y, z + float q bits
+    const void *cols_b;         // optional: section B lives in a separate array (else it follows A)
     int n_tiles_a;              // tiles in section A (cores)
     int n_tiles;                // total tiles (A then B)
     // output
@@ -69,6 +70,7 @@ constexpr int kGateDone = 1, kGatePhase64 = 2, kGatePhaseMixed = 4;
 int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, cudaStream_t st);
 int launch_pair_mixed(const PairArgs &a, cudaStream_t st);
 int launch_pair_static(const PairArgs &a, cudaStream_t st);
+int launch_pair_fp64_two_fields(const PairArgs &a, cudaStream_t st);
 int fp64_rows_per_block();
 
 }  // namespace upol
@@ -92,6 +94,7 @@ struct upol_system {
     double *qc = nullptr, *qs = nullptr, *k = nullptr;   // [nsite]
     // device: per-Drude-row (compact)
     int *row_site = nullptr;      // [nd] site of the row
+    int *site_row = nullptr;      // [nsite] Drude row of a site, -1 if not polarisable
     double *row_qs = nullptr, *row_k = nullptr;           // [nd]
     int *exA_lo = nullptr, *exA_len = nullptr, *exB_lo = nullptr, *exB_len = nullptr;   // [nd_pad]
     double *rowx = nullptr, *rowy = nullptr, *rowz = nullptr;     // [nd_pad] shell positions
@@ -119,6 +122,12 @@ struct upol_system {
     double *energy = nullptr;     // [UPOL_E_SIZE] device result of the last evaluation
     double *e_static = nullptr;   // [2] device: d-independent part summed over rows (informational)
     double *phi_static = nullptr; // [nd_pad] device: per-row static potential, subtracted row by row
+    // core-force pass (allocated on first use): Drude-core columns (r_i, qs_i), site-row tables, scratch
+    double4 *cols_dcore = nullptr;   // [nb_pad]
+    double *site_x = nullptr, *site_y = nullptr, *site_z = nullptr;   // [ns_pad]
+    int *exS_lo = nullptr, *exS_len = nullptr, *exS2_lo = nullptr;    // [ns_pad] excluded Drude rows of the site's molecule
+    double *cf_tmp = nullptr;        // [6*nd + 6*nsite] folded fields
+    int64_t ns_pad = 0;
     bool static_valid = false;
 
     // row shard (Drude rows of molecules [mol_lo, mol_hi))
@@ -169,6 +178,7 @@ void set_box(upol_system *s, const double *lo, const double *hi);
 int sys_box_from_device(upol_system *s, cudaStream_t st);
 int sys_make_sij(const double *rij, const double *u, int u_is_scalar, int64_t n, double *out, cudaStream_t st);
 int sys_coulomb_static(upol_system *s, double *out2, cudaStream_t st);
+int sys_core_forces(upol_system *s, const double *d_compact, double *dudr_full, cudaStream_t st);
 const char *last_error_message();
 
 // collectives (comm.cu)

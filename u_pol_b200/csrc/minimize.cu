@@ -557,17 +557,20 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
         }
         buf ^= 1;
     }
-    // final state + fp64 energy at the minimiser (x is complete on every rank)
+    // fp64 energy at the minimiser (x is complete on every rank).  The gradient there is already
+    // known from the last slot (its norm is in the control block), so this is a potential-only pass.
     EvalOpts ef;
     ef.precision = UPOL_FP64;
-    ef.want_energy = true; ef.want_grad = true; ef.reduce_ranks = true;
+    ef.want_energy = true; ef.want_grad = false; ef.reduce_ranks = true;
     rc = sys_eval_compact(s, x, ef, w->e_final, w->g, st);
     if (rc) return rc;
     UPOL_CUDA(cudaMemcpyAsync(w->h_ic, w->ic, sizeof(int) * I_SIZE, cudaMemcpyDeviceToHost, st));
     UPOL_CUDA(cudaMemcpyAsync(w->h_sc, w->e_final, sizeof(double) * UPOL_E_SIZE, cudaMemcpyDeviceToHost, st));
+    UPOL_CUDA(cudaMemcpyAsync(w->h_sc + D_SIZE, w->sc, sizeof(double) * D_SIZE, cudaMemcpyDeviceToHost, st));
     UPOL_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < UPOL_E_SIZE; ++i) res->energy[i] = w->h_sc[i];
-    res->gnorm = std::sqrt(res->energy[UPOL_E_GNORM2]);
+    res->gnorm = w->h_sc[D_SIZE + D_GNORM];
+    res->energy[UPOL_E_GNORM2] = res->gnorm * res->gnorm;
     res->iterations = w->h_ic[I_ITER];
     res->evaluations = w->h_ic[I_NEVAL] + 1;
     res->flags = w->h_ic[I_FLAGS];

@@ -63,7 +63,9 @@ __device__ __forceinline__ double rsqrt_f64(double x) {
     return fma(q, p, y);
 }
 
-template <int ROWS, bool POT, bool GRAD, int MINB>
+// SPLITF (core-force pass): the fields of section A and section B are kept apart, because they are
+// multiplied by different charges of the row afterwards (output comps 0-2 and 3-5, no potential).
+template <int ROWS, bool POT, bool GRAD, int MINB, bool SPLITF = false>
 __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs a) {
     __shared__ double4 sh[kTileCols];
     if (a.gate != nullptr && (*a.gate & a.gate_skip_mask) != 0) return;   // minimiser: converged / other phase
@@ -87,14 +89,25 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
 
     const int t0 = (int)(((int64_t)a.n_tiles * blockIdx.y) / a.n_split);
     const int t1 = (int)(((int64_t)a.n_tiles * (blockIdx.y + 1)) / a.n_split);
+    const double4 *__restrict__ cols_b = static_cast<const double4 *>(a.cols_b);
+    double gx[SPLITF ? ROWS : 1], gy[SPLITF ? ROWS : 1], gz[SPLITF ? ROWS : 1];   // section A field once B starts
+    if (SPLITF) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) gx[r] = gy[r] = gz[r] = 0.0;
+    }
 
     for (int t = t0; t < t1; ++t) {
         const int base = t * kTileCols;
-        __syncthreads();
-        for (int j = tid; j < kTileCols; j += kBlock) sh[j] = cols[base + j];
-        __syncthreads();
-
         const bool isB = t >= a.n_tiles_a;
+        const double4 *src = (cols_b != nullptr && isB) ? cols_b + (int64_t)(t - a.n_tiles_a) * kTileCols : cols + base;
+        __syncthreads();
+        for (int j = tid; j < kTileCols; j += kBlock) sh[j] = src[j];
+        __syncthreads();
+        if (SPLITF && t == a.n_tiles_a) {
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) { gx[r] = fx[r]; gy[r] = fy[r]; gz[r] = fz[r]; fx[r] = fy[r] = fz[r] = 0.0; }
+        }
+
         bool need = false;
         int lo[ROWS], len[ROWS];
 #pragma unroll
@@ -172,6 +185,17 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
     for (int r = 0; r < ROWS; ++r) {
         const int lr = row_base + r * kBlock;
         if (lr < a.n_rows) {
+            if (SPLITF) {
+                // the split of this block saw B tiles iff t1 > n_tiles_a; before that fx IS the A field
+                const bool sawB = t1 > a.n_tiles_a;
+                out[0 * a.part_stride + lr] = sawB ? gx[r] : fx[r];
+                out[1 * a.part_stride + lr] = sawB ? gy[r] : fy[r];
+                out[2 * a.part_stride + lr] = sawB ? gz[r] : fz[r];
+                out[3 * a.part_stride + lr] = sawB ? fx[r] : 0.0;
+                out[4 * a.part_stride + lr] = sawB ? fy[r] : 0.0;
+                out[5 * a.part_stride + lr] = sawB ? fz[r] : 0.0;
+                continue;
+            }
             if (POT) {
                 out[0 * a.part_stride + lr] = phA[r] + plA[r];
                 out[1 * a.part_stride + lr] = phB[r] + plB[r];
@@ -216,7 +240,7 @@ template <int ROWS>
 __global__ void __launch_bounds__(kBlock) pair_static_kernel(const PairArgs a) {
     __shared__ double4 sh[kTileCols];
     __shared__ double sh2[kTileCols];
-    const double4 *__restrict__ cols = static_cast<const double4 *>(a.cols);   // centred x, y, z, q_eff
+    const double4 *__restrict__ cols = static_cast<const double4 *>(a.cols);   // x, y, z, q_eff (centred at staging)
 
     const int tid = threadIdx.x;
     const int row_base = blockIdx.x * (kBlock * ROWS) + tid;
@@ -238,7 +262,8 @@ __global__ void __launch_bounds__(kBlock) pair_static_kernel(const PairArgs a) {
         const int base = t * kTileCols;
         __syncthreads();
         for (int j = tid; j < kTileCols; j += kBlock) {
-            const double4 c = cols[base + j];
+            double4 c = cols[base + j];
+            c.x -= a.cx; c.y -= a.cy; c.z -= a.cz;
             sh[j] = c;
             sh2[j] = fma(c.z, c.z, fma(c.y, c.y, c.x * c.x));
         }
@@ -419,6 +444,14 @@ int fp64_rows_per_block() { return kRowTile; }
 int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, cudaStream_t st) {
     if (a.n_rows <= 0) return UPOL_OK;
     launch_fp64_variant<kRowsPerThread, 1>(a, with_pot, with_grad, st);
+    UPOL_CUDA(cudaGetLastError());
+    return UPOL_OK;
+}
+
+int launch_pair_fp64_two_fields(const PairArgs &a, cudaStream_t st) {
+    if (a.n_rows <= 0) return UPOL_OK;
+    dim3 grid((unsigned)((a.n_rows + kRowTile - 1) / kRowTile), (unsigned)a.n_split);
+    pair_fp64_kernel<kRowsPerThread, false, true, 1, true><<<grid, kBlock, 0, st>>>(a);
     UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
 }

@@ -46,7 +46,7 @@ __global__ void build_core_columns_kernel(int nsite, int na_pad, const double *_
         const double x = r[3 * i], y = r[3 * i + 1], z = r[3 * i + 2];
         cols[i] = make_double4(x, y, z, qc[i]);
         cols_f[mix_slot[i]] = fix_col(x - cx, y - cy, z - cz, inv_grid, qc[i]);
-        cols_static[i] = make_double4(x - cx, y - cy, z - cz, qc[i] + 0.5 * qs[i]);
+        cols_static[i] = make_double4(x, y, z, qc[i] + 0.5 * qs[i]);
     } else {
         cols[i] = make_double4(kFar, kFar, kFar, 0.0);
         cols_static[i] = make_double4(kFar, kFar, kFar, 0.0);
@@ -120,7 +120,7 @@ constexpr int kFinLanes = kFinBlock / kFinRows;
 // count reaches ~100 and a single thread per row would chain ~500 L2 loads.
 template <int NC>
 __device__ __forceinline__ void fold_splits(const double *__restrict__ part, int64_t stride, int lr, bool live,
-                                            int n_split, int c0, double (*sm)[kFinRows][5], double *out) {
+                                            int n_split, int c0, double (*sm)[kFinRows][kPartComps], double *out) {
     const int lx = threadIdx.x % kFinRows, ly = threadIdx.x / kFinRows;
     double acc[NC];
 #pragma unroll
@@ -155,7 +155,7 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
                      const double *__restrict__ th_u, const double *__restrict__ phi_static,
                      bool with_grad, double *__restrict__ gc, double *__restrict__ eblock) {
     __shared__ double sm[kFinBlock / 32];
-    __shared__ double fold[kFinLanes][kFinRows][5];
+    __shared__ double fold[kFinLanes][kFinRows][kPartComps];
     const int gw = gate ? *gate : 0;
     if (gw & kGateDone) return;
     // which field kernel ran decides how many column splits hold force partials
@@ -222,7 +222,7 @@ finalize_static_kernel(int n_rows, int row0, int n_split, const double *__restri
                        const double *__restrict__ row_qs, double *__restrict__ phi_static,
                        double *__restrict__ eblock) {
     __shared__ double sm[kFinBlock / 32];
-    __shared__ double fold[kFinLanes][kFinRows][5];
+    __shared__ double fold[kFinLanes][kFinRows][kPartComps];
     const int lr = blockIdx.x * kFinRows + threadIdx.x % kFinRows;
     const bool live = lr < n_rows;
     double pot[1] = {0.0};
@@ -553,7 +553,7 @@ finalize_sites_kernel(int nsite, int n_split, const double *__restrict__ part, i
                       const double *__restrict__ qc, const double *__restrict__ qs, int total,
                       double *__restrict__ eblock) {
     __shared__ double sm[kFinBlock / 32];
-    __shared__ double fold[kFinLanes][kFinRows][5];
+    __shared__ double fold[kFinLanes][kFinRows][kPartComps];
     const int i = blockIdx.x * kFinRows + threadIdx.x % kFinRows;
     const bool live = i < nsite;
     double pot[1] = {0.0};
@@ -607,6 +607,147 @@ int sys_coulomb_static(upol_system *s, double *out2, cudaStream_t st) {
     UPOL_CUDA(cudaGetLastError());
     UPOL_CUDA(cudaStreamSynchronize(st));   // hex (host vector) and the scratch die here
     cudaFree(rows); cudaFree(ex); cudaFree(cols); cudaFree(part); cudaFree(eblock);
+    return UPOL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Core forces: dU_ind/dr_i at fixed displacements (SURVEY 8f "next" #3, first half).  The reference
+// has no such function; it is what an MD code needs to move the cores on the U_ind surface.
+//   dU/dr_a = [a Drude] K qs_a (F_a - H_a)  +  K qc_a G_a  -  K (qc_a + qs_a/2) H'_a  +  intra
+// F_a : field at the shell s_a from all other-molecule charges        (main pass, field only)
+// H_a : field at the core r_a from the static charges qc + qs/2        (static columns, field)
+// G_a : field at r_a from the other molecules' shells (qs at s)        } one pass over all site rows,
+// H'_a: field at r_a from the other molecules' Drude CORES (qs at r)   } two fields kept apart
+// intra: all four Thole terms of a screened pair depend on R = r_b - r_a alike.
+// ---------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(kFinBlock)
+fold_fields_kernel(int n_rows, int n_split, const double *__restrict__ part, int64_t stride, int c0,
+                   double *__restrict__ dst) {
+    __shared__ double fold[kFinLanes][kFinRows][kPartComps];
+    const int lr = blockIdx.x * kFinRows + threadIdx.x % kFinRows;
+    const bool live = lr < n_rows;
+    double v[NC];
+    fold_splits<NC>(part, stride, lr, live, n_split, c0, fold, v);
+    if (live && threadIdx.x < kFinRows) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) dst[(int64_t)c * n_rows + lr] = v[c];
+    }
+}
+
+__global__ void build_force_tables_kernel(int nsite, int nd, int nb_pad, const double *__restrict__ r,
+                                          const int *__restrict__ row_site, const double *__restrict__ row_qs,
+                                          double *__restrict__ sx, double *__restrict__ sy, double *__restrict__ sz,
+                                          double4 *__restrict__ cols_dcore) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nsite) { sx[i] = r[3 * i]; sy[i] = r[3 * i + 1]; sz[i] = r[3 * i + 2]; }
+    if (i < nb_pad) {
+        if (i < nd) { const int s = row_site[i]; cols_dcore[i] = make_double4(r[3 * s], r[3 * s + 1], r[3 * s + 2], row_qs[i]); }
+        else cols_dcore[i] = make_double4(kFar, kFar, kFar, 0.0);
+    }
+}
+
+__global__ void core_force_assemble_kernel(int nsite, int nd, const double *__restrict__ r, const double *__restrict__ dc,
+                                           const double *__restrict__ qc, const double *__restrict__ qs,
+                                           const int *__restrict__ site_row, const int *__restrict__ row_site,
+                                           const double *__restrict__ row_qs, const int *__restrict__ th_ptr,
+                                           const int *__restrict__ th_row, const double *__restrict__ th_u,
+                                           const double *__restrict__ F, const double *__restrict__ H,
+                                           const double *__restrict__ GH, double *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nsite) return;
+    const double qe = qc[j] + 0.5 * qs[j];
+    double g[3];
+    for (int c = 0; c < 3; ++c) g[c] = kCoulomb * (qc[j] * GH[(int64_t)c * nsite + j] - qe * GH[(int64_t)(3 + c) * nsite + j]);
+    const int a = site_row[j];
+    if (a >= 0) {
+        const double q = row_qs[a];
+        for (int c = 0; c < 3; ++c) g[c] += kCoulomb * q * (F[(int64_t)c * nd + a] - H[(int64_t)c * nd + a]);
+        const double dx = dc[3 * a], dy = dc[3 * a + 1], dz = dc[3 * a + 2];
+        for (int p = th_ptr[a]; p < th_ptr[a + 1]; ++p) {
+            const int b = th_row[p], sb = row_site[b];
+            const double u = th_u[p];
+            const double Rx = r[3 * sb] - r[3 * j], Ry = r[3 * sb + 1] - r[3 * j + 1], Rz = r[3 * sb + 2] - r[3 * j + 2];
+            const double bx = dc[3 * b], by = dc[3 * b + 1], bz = dc[3 * b + 2];
+            const double Ax = Rx + dx, Ay = Ry + dy, Az = Rz + dz, Bx = Rx - bx, By = Ry - by, Bz = Rz - bz;
+            const double Cx = Ax - bx, Cy = Ay - by, Cz = Az - bz;
+            double gR, gA, gB, gC, cR, cA, cB, cC;
+            thole_g(Rx, Ry, Rz, u, gR, cR); thole_g(Ax, Ay, Az, u, gA, cA);
+            thole_g(Bx, By, Bz, u, gB, cB); thole_g(Cx, Cy, Cz, u, gC, cC);
+            const double qq = kCoulomb * q * row_qs[b];
+            // d/dr_a of qq [g(R) - g(A) - g(B) + g(C)] with R = r_b - r_a: minus the gradient w.r.t. R
+            g[0] -= qq * (cR * Rx - cA * Ax - cB * Bx + cC * Cx);
+            g[1] -= qq * (cR * Ry - cA * Ay - cB * By + cC * Cy);
+            g[2] -= qq * (cR * Rz - cA * Az - cB * Bz + cC * Cz);
+        }
+    }
+    out[3 * j] = g[0]; out[3 * j + 1] = g[1]; out[3 * j + 2] = g[2];
+}
+
+int sys_core_forces(upol_system *s, const double *dcmp, double *dudr, cudaStream_t st) {
+    if (s->nranks > 1) return UPOL_ERR_ARG;     // single-rank for now (columns and rows are all local)
+    const int64_t n = s->nsite, nd = s->nd;
+    if (!s->cf_tmp) {      // first use: tables of the site-row pass
+        s->ns_pad = round_up(n, 512);
+        UPOL_CUDA(cudaMalloc((void **)&s->cols_dcore, sizeof(double4) * s->nb_pad));
+        UPOL_CUDA(cudaMalloc((void **)&s->site_x, sizeof(double) * 3 * s->ns_pad));
+        s->site_y = s->site_x + s->ns_pad; s->site_z = s->site_y + s->ns_pad;
+        UPOL_CUDA(cudaMalloc((void **)&s->exS_lo, sizeof(int) * 3 * s->ns_pad));
+        s->exS_len = s->exS_lo + s->ns_pad; s->exS2_lo = s->exS_len + s->ns_pad;
+        UPOL_CUDA(cudaMalloc((void **)&s->cf_tmp, sizeof(double) * (6 * std::max<int64_t>(nd, 1) + 6 * n)));
+        std::vector<int> ex(3 * s->ns_pad, 0);
+        for (int64_t j = 0; j < n; ++j) {
+            const int m = s->h_mol[j];
+            ex[j] = s->h_mol_row0[m]; ex[s->ns_pad + j] = s->h_mol_nrow[m]; ex[2 * s->ns_pad + j] = (int)s->nb_pad + s->h_mol_row0[m];
+        }
+        UPOL_CUDA(cudaMemcpy(s->exS_lo, ex.data(), sizeof(int) * ex.size(), cudaMemcpyHostToDevice));
+        UPOL_CUDA(cudaMemset(s->site_x, 0, sizeof(double) * 3 * s->ns_pad));
+    }
+    UPOL_CUDA(cudaMemsetAsync(dudr, 0, sizeof(double) * 3 * n, st));
+    if (nd == 0) return UPOL_OK;
+    double *F = s->cf_tmp, *H = F + 3 * nd, *GH = H + 3 * nd;
+    prepare_shells_kernel<<<nblk(s->nb_pad, 256), 256, 0, st>>>(
+        (int)nd, (int)s->nb_pad, s->row_site, s->r, dcmp, s->row_qs, s->centre[0], s->centre[1], s->centre[2],
+        s->inv_grid, s->mix_slot, s->rowx, s->rowy, s->rowz, s->cols + s->na_pad, s->cols_f);
+    build_force_tables_kernel<<<nblk(std::max<int64_t>(n, s->nb_pad), 256), 256, 0, st>>>(
+        (int)n, (int)nd, (int)s->nb_pad, s->r, s->row_site, s->row_qs, s->site_x, s->site_y, s->site_z, s->cols_dcore);
+    const int nbf = (int)nblk(nd, kFinRows);
+    {   // F: field at the shells (main pass, field only)
+        PairArgs a = base_args(s);
+        a.n_rows = (int)nd; a.row0 = 0; a.part_stride = part_stride_for(nd);
+        a.rx = s->rowx; a.ry = s->rowy; a.rz = s->rowz;
+        a.cols = s->cols; a.n_tiles = (int)((s->na_pad + s->nb_pad) / kTileCols);
+        a.n_split = choose_split(s, nd, a.n_tiles, fp64_rows_per_block());
+        int rc = launch_pair_fp64(a, false, true, st);
+        if (rc) return rc;
+        fold_fields_kernel<3><<<nbf, kFinBlock, 0, st>>>((int)nd, a.n_split, s->part, a.part_stride, 2, F);
+    }
+    {   // H: field at the Drude cores from the static charges
+        PairArgs a = base_args(s);
+        a.n_rows = (int)nd; a.row0 = 0; a.part_stride = part_stride_for(nd);
+        a.rx = s->srowx; a.ry = s->srowy; a.rz = s->srowz;
+        a.cols = s->cols_static; a.n_tiles = a.n_tiles_a;
+        a.n_split = choose_split(s, nd, a.n_tiles, fp64_rows_per_block());
+        int rc = launch_pair_fp64(a, false, true, st);
+        if (rc) return rc;
+        fold_fields_kernel<3><<<nbf, kFinBlock, 0, st>>>((int)nd, a.n_split, s->part, a.part_stride, 2, H);
+    }
+    {   // G, H': fields at every core from the other molecules' shells / Drude cores
+        PairArgs a = base_args(s);
+        a.n_rows = (int)n; a.row0 = 0; a.part_stride = part_stride_for(n);
+        a.rx = s->site_x; a.ry = s->site_y; a.rz = s->site_z;
+        a.exA_lo = s->exS_lo; a.exA_len = s->exS_len; a.exB_lo = s->exS2_lo; a.exB_len = s->exS_len;
+        a.cols = s->cols + s->na_pad;           // shells (refreshed by prepare_shells above)
+        a.cols_b = s->cols_dcore;
+        a.n_tiles_a = (int)(s->nb_pad / kTileCols); a.n_tiles = 2 * a.n_tiles_a;
+        a.n_split = choose_split(s, n, a.n_tiles, fp64_rows_per_block());
+        int rc = launch_pair_fp64_two_fields(a, st);
+        if (rc) return rc;
+        fold_fields_kernel<6><<<nblk(n, kFinRows), kFinBlock, 0, st>>>((int)n, a.n_split, s->part, a.part_stride, 0, GH);
+    }
+    core_force_assemble_kernel<<<nblk(n, 128), 128, 0, st>>>((int)n, (int)nd, s->r, dcmp, s->qc, s->qs, s->site_row,
+                                                             s->row_site, s->row_qs, s->th_ptr, s->th_row, s->th_u, F, H, GH, dudr);
+    UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
 }
 

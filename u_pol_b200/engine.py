@@ -152,6 +152,16 @@ class UindSystem:
                 "upol_uind_energy_grad_host")
         return e, (g.reshape(self.nsite, 3) if want_grad else None)
 
+    def core_gradient(self, d):
+        """dU_ind/dr_core at fixed displacements, (N,3) on device (force on the cores = minus this).
+        Not in the reference (SURVEY 8f next #3)."""
+        with torch.cuda.device(self.device):
+            dd = self._dev_f64(d, 3 * self.nsite)
+            out = torch.empty(self.nsite, 3, dtype=torch.float64, device=self.device)
+            L.check(L.lib().upol_uind_core_gradient_dev(self._h, dd.data_ptr(), out.data_ptr(), self._stream()),
+                    "upol_uind_core_gradient_dev")
+        return out
+
     def coulomb_static(self):
         """(K sum qc qc / R, K sum Q Q / R) over inter-molecular pairs, on device."""
         with torch.cuda.device(self.device):
