@@ -136,6 +136,7 @@ def cpu_sample(s, d, target_seconds):
     Returns (site_pairs_per_s, cores, description)."""
     from oracle import c_oracle
 
+    c_oracle.use_all_cores()
     n = s.nmol * s.natoms
     rows = 64 * s.natoms
     t0 = time.perf_counter()
@@ -157,6 +158,7 @@ def run_reference(args):
         return
     from oracle import c_oracle
 
+    c_oracle.use_all_cores()          # torchrun exports OMP_NUM_THREADS=1 to its workers
     s, d = make_workload()
     n = s.nmol * s.natoms
     # size one step to ~2 s of host work
@@ -261,10 +263,12 @@ def run_cuda(args):
     e_host = e.cpu().numpy()
 
     # ---- end to end through the C ABI with host buffers (H2D of r and d, D2H of E and grad) --
-    r_host = np.ascontiguousarray(s.r_core.reshape(-1))
-    d_flat = np.ascontiguousarray(d_host.reshape(-1))
-    e_out = np.empty(L.E_SIZE)
-    g_out = np.empty(3 * n)
+    # page-locked host buffers (the contract: inputs come from pinned host memory)
+    r_pin = torch.from_numpy(np.ascontiguousarray(s.r_core.reshape(-1))).pin_memory()
+    d_pin = torch.from_numpy(np.ascontiguousarray(d_host.reshape(-1))).pin_memory()
+    e_pin = torch.empty(L.E_SIZE, dtype=torch.float64).pin_memory()
+    g_pin = torch.empty(3 * n, dtype=torch.float64).pin_memory()
+    r_host, d_flat, e_out, g_out = r_pin.numpy(), d_pin.numpy(), e_pin.numpy(), g_pin.numpy()
     lib = L.lib()
 
     def e2e_step():

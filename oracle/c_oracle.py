@@ -31,6 +31,13 @@ def max_threads():
     return int(lib().upol_oracle_max_threads())
 
 
+def use_all_cores():
+    """Undo an inherited OMP_NUM_THREADS=1 (torchrun sets it for its workers)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().upol_oracle_set_threads(int(n))
+    return max_threads()
+
+
 def energy_grad(r_core, d, q_core, q_shell, k, thole_u=None, row_lo=0, row_hi=None, want_grad=True):
     """r_core, d: (nmol,natoms,3); q_core, q_shell, k: (nmol,natoms); thole_u (nmol,natoms,natoms)|None.
     Returns (energy[4] = [U_ind, U_coul, U_coul_static, U_self] shares of the rows, grad (nmol,natoms,3))."""

@@ -44,6 +44,15 @@ double upol_oracle_one_4pi_eps0(void) {
     return 1 / (4 * M_PI_REF * eps0);
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm asks for all cores back. */
+void upol_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int upol_oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -50,6 +50,13 @@ void free_system(upol_system *s) {
     delete s;
 }
 
+// true if `p` is page-locked host memory (then the library copies straight from / to it)
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 void compute_centre(upol_system *s, const double *r_host) {
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int64_t i = 0; i < s->nsite; ++i)
@@ -254,6 +261,13 @@ int upol_system_set_positions(upol_system *s, const double *r_core, void *stream
     const size_t n3 = 3 * (size_t)s->nsite;
     int rc = sys_ensure_pinned(s, sizeof(double) * (2 * n3 + UPOL_E_SIZE));
     if (rc) return rc;
+    if (is_pinned(r_core)) {                              // page-locked caller buffer: copy straight from it
+        UPOL_CUDA(cudaMemcpyAsync(s->r, r_core, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
+        rc = sys_upload_positions(s, nullptr, st);
+        if (rc) return rc;
+        UPOL_CUDA(cudaStreamSynchronize(st));             // the caller may reuse its buffer on return
+        return UPOL_OK;
+    }
     UPOL_CUDA(cudaStreamSynchronize(st));                 // staging buffer may still be in flight
     memcpy(s->pin, r_core, sizeof(double) * n3);
     UPOL_CUDA(cudaMemcpyAsync(s->r, s->pin, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
@@ -327,17 +341,19 @@ int upol_uind_energy_grad_host(upol_system *s, const double *d, int precision, d
     rc = sys_ensure_hscratch(s, 2 * n3 + UPOL_E_SIZE);
     if (rc) return rc;
     double *dfull = s->hscratch, *gfull = dfull + n3, *e_dev = gfull + n3;
+    // page-locked caller buffers are used directly; pageable ones are staged through the library's own
+    const bool d_pin = is_pinned(d), g_pin = grad && is_pinned(grad), e_pin = energy && is_pinned(energy);
     double *pd = s->pin, *pg = s->pin + n3, *pe = pg + n3;
-    memcpy(pd, d, sizeof(double) * n3);
+    if (!d_pin) memcpy(pd, d, sizeof(double) * n3);
     cudaStream_t st = 0;
-    UPOL_CUDA(cudaMemcpyAsync(dfull, pd, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
+    UPOL_CUDA(cudaMemcpyAsync(dfull, d_pin ? d : pd, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
     rc = upol_uind_energy_grad_dev(s, dfull, precision, energy ? e_dev : nullptr, grad ? gfull : nullptr, st);
     if (rc) return rc;
-    if (energy) UPOL_CUDA(cudaMemcpyAsync(pe, e_dev, sizeof(double) * UPOL_E_SIZE, cudaMemcpyDeviceToHost, st));
-    if (grad) UPOL_CUDA(cudaMemcpyAsync(pg, gfull, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
+    if (energy) UPOL_CUDA(cudaMemcpyAsync(e_pin ? energy : pe, e_dev, sizeof(double) * UPOL_E_SIZE, cudaMemcpyDeviceToHost, st));
+    if (grad) UPOL_CUDA(cudaMemcpyAsync(g_pin ? grad : pg, gfull, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
     UPOL_CUDA(cudaStreamSynchronize(st));
-    if (energy) memcpy(energy, pe, sizeof(double) * UPOL_E_SIZE);
-    if (grad) memcpy(grad, pg, sizeof(double) * n3);
+    if (energy && !e_pin) memcpy(energy, pe, sizeof(double) * UPOL_E_SIZE);
+    if (grad && !g_pin) memcpy(grad, pg, sizeof(double) * n3);
     return UPOL_OK;
 }
 
