@@ -116,12 +116,48 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
             len[r] = isB ? lenB[r] : lenA[r];
             need |= (lo[r] < kTileCols) && (lo[r] + len[r] > 0);
         }
-        double ph[ROWS];
+        // tile-local sums: the compare-free loop below is speculative and may have to be redone
+        double ph[ROWS], tx[ROWS], ty[ROWS], tz[ROWS];
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) ph[r] = 0.0;
+        for (int r = 0; r < ROWS; ++r) ph[r] = tx[r] = ty[r] = tz[r] = 0.0;
 
-        if (__any_sync(0xffffffffu, need)) {
-            // predicated tile: same-molecule columns masked out
+        bool careful = __any_sync(0xffffffffu, need);
+        if (!careful) {
+            // no same-molecule column in this tile for any row of the warp.  No per-pair selects either:
+            // only an integer min of the high word of r^2 (ALU pipe); a zero-distance pair
+            // (polarization.py:33-42: term dropped) is caught after the tile, which is then redone
+            // with the predicated loop - the sums are tile-local, so nothing has to be undone.
+            int hmin = 0x7fffffff;
+#pragma unroll 4
+            for (int j = 0; j < kTileCols; ++j) {
+                const double4 c = sh[j];
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const double dx = c.x - sx[r], dy = c.y - sy[r], dz = c.z - sz[r];
+                    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    hmin = min(hmin, __double2hiint(r2));
+                    if (POT) {
+                        const double inv = rsqrt_f64(r2);
+                        const double tq = c.w * inv;
+                        ph[r] += tq;
+                        if (GRAD) {
+                            const double w = tq * (inv * inv);
+                            tx[r] = fma(w, dx, tx[r]); ty[r] = fma(w, dy, ty[r]); tz[r] = fma(w, dz, tz[r]);
+                        }
+                    } else {
+                        const double w = q_over_r3_f64(c.w, r2);
+                        tx[r] = fma(w, dx, tx[r]); ty[r] = fma(w, dy, ty[r]); tz[r] = fma(w, dz, tz[r]);
+                    }
+                }
+            }
+            careful = __any_sync(0xffffffffu, hmin < 0x00100000);      // zero or subnormal r^2
+            if (careful) {
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) ph[r] = tx[r] = ty[r] = tz[r] = 0.0;
+            }
+        }
+        if (careful) {
+            // predicated tile: same-molecule columns and zero-distance pairs masked out
 #pragma unroll 2
             for (int j = 0; j < kTileCols; ++j) {
                 const double4 c = sh[j];
@@ -129,7 +165,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
                 for (int r = 0; r < ROWS; ++r) {
                     const double dx = c.x - sx[r], dy = c.y - sy[r], dz = c.z - sz[r];
                     double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    const bool drop = ((unsigned)(j - lo[r]) < (unsigned)len[r]) || (__double2hiint(r2) == 0);
+                    const bool drop = ((unsigned)(j - lo[r]) < (unsigned)len[r]) || (__double2hiint(r2) < 0x00100000);
                     const double q = drop ? 0.0 : c.w;
                     r2 = drop ? 1.0 : r2;
                     if (POT) {
@@ -138,39 +174,18 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
                         ph[r] += tq;
                         if (GRAD) {
                             const double w = tq * (inv * inv);
-                            fx[r] = fma(w, dx, fx[r]); fy[r] = fma(w, dy, fy[r]); fz[r] = fma(w, dz, fz[r]);
+                            tx[r] = fma(w, dx, tx[r]); ty[r] = fma(w, dy, ty[r]); tz[r] = fma(w, dz, tz[r]);
                         }
                     } else {
                         const double w = q_over_r3_f64(q, r2);
-                        fx[r] = fma(w, dx, fx[r]); fy[r] = fma(w, dy, fy[r]); fz[r] = fma(w, dz, fz[r]);
+                        tx[r] = fma(w, dx, tx[r]); ty[r] = fma(w, dy, ty[r]); tz[r] = fma(w, dz, tz[r]);
                     }
                 }
             }
-        } else {
-#pragma unroll 4
-            for (int j = 0; j < kTileCols; ++j) {
-                const double4 c = sh[j];
+        }
+        if (GRAD) {
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    const double dx = c.x - sx[r], dy = c.y - sy[r], dz = c.z - sz[r];
-                    double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    const bool drop = (__double2hiint(r2) == 0);   // zero distance: term dropped
-                    const double q = drop ? 0.0 : c.w;
-                    r2 = drop ? 1.0 : r2;
-                    if (POT) {
-                        const double inv = rsqrt_f64(r2);
-                        const double tq = q * inv;
-                        ph[r] += tq;
-                        if (GRAD) {
-                            const double w = tq * (inv * inv);
-                            fx[r] = fma(w, dx, fx[r]); fy[r] = fma(w, dy, fy[r]); fz[r] = fma(w, dz, fz[r]);
-                        }
-                    } else {
-                        const double w = q_over_r3_f64(q, r2);
-                        fx[r] = fma(w, dx, fx[r]); fy[r] = fma(w, dy, fy[r]); fz[r] = fma(w, dz, fz[r]);
-                    }
-                }
-            }
+            for (int r = 0; r < ROWS; ++r) { fx[r] += tx[r]; fy[r] += ty[r]; fz[r] += tz[r]; }
         }
         if (POT) {
 #pragma unroll
@@ -278,7 +293,31 @@ __global__ void __launch_bounds__(kBlock) pair_static_kernel(const PairArgs a) {
         double pt[ROWS];
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) pt[r] = 0.0;
-        if (__any_sync(0xffffffffu, need)) {
+        bool careful = __any_sync(0xffffffffu, need);
+        if (!careful) {
+            // speculative compare-free loop: no per-pair selects, only an integer min of the high word
+            // of r^2 (ALU pipe).  A zero-distance pair (r^2 below the cancellation noise) is caught
+            // after the tile and the tile is redone with the predicated loop; pt is tile-local, so
+            // nothing has to be undone.
+            int hmin = 0x7fffffff;
+#pragma unroll 4
+            for (int j = 0; j < kTileCols; ++j) {
+                const double4 c = sh[j];
+                const double x2 = sh2[j];
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const double r2 = fma(mx[r], c.x, fma(my[r], c.y, fma(mz[r], c.z, x2 + r2i[r])));
+                    hmin = min(hmin, __double2hiint(r2));
+                    pt[r] = fma(c.w, rsqrt_f64(r2), pt[r]);
+                }
+            }
+            careful = __any_sync(0xffffffffu, hmin < 0x3DDB7CDF);
+            if (careful) {
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) pt[r] = 0.0;
+            }
+        }
+        if (careful) {
 #pragma unroll 2
             for (int j = 0; j < kTileCols; ++j) {
                 const double4 c = sh[j];
@@ -288,20 +327,6 @@ __global__ void __launch_bounds__(kBlock) pair_static_kernel(const PairArgs a) {
                     double r2 = fma(mx[r], c.x, fma(my[r], c.y, fma(mz[r], c.z, x2 + r2i[r])));
                     // zero distance (|r| < 1e-5 nm once the cancellation noise is allowed for): dropped
                     const bool drop = ((unsigned)(j - rel[r]) < (unsigned)len[r]) || (__double2hiint(r2) < 0x3DDB7CDF);
-                    const double q = drop ? 0.0 : c.w;
-                    r2 = drop ? 1.0 : r2;
-                    pt[r] = fma(q, rsqrt_f64(r2), pt[r]);
-                }
-            }
-        } else {
-#pragma unroll 4
-            for (int j = 0; j < kTileCols; ++j) {
-                const double4 c = sh[j];
-                const double x2 = sh2[j];
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    double r2 = fma(mx[r], c.x, fma(my[r], c.y, fma(mz[r], c.z, x2 + r2i[r])));
-                    const bool drop = (__double2hiint(r2) < 0x3DDB7CDF);
                     const double q = drop ? 0.0 : c.w;
                     r2 = drop ? 1.0 : r2;
                     pt[r] = fma(q, rsqrt_f64(r2), pt[r]);
