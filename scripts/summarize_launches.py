@@ -1,5 +1,6 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel."""
-import collections, csv, sys
+import collections, csv, signal, sys
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 rows = list(csv.DictReader(l for l in open(sys.argv[1]) if l.startswith('"')))
 agg = collections.defaultdict(lambda: [0, 0.0])
 for r in rows:
