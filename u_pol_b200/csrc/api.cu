@@ -178,11 +178,15 @@ int upol_system_create(upol_system **out, int device, int64_t nsite, const doubl
     }
     s->npair_ordered = (int64_t)th_row.size();
 
-    // Column splits S are chosen per launch so that (row blocks * S) ~ 148*8 (choose_split);
-    // with rb row blocks of <= 512 rows, S*stride <= (1184/rb + 1)(512 rb + 511), which the
-    // allocation below covers for the full system and for every row shard of it.
+    // Column splits S are chosen per launch so that (row blocks * S) ~ 148*40 (choose_split);
+    // with rb row blocks of <= 512 rows, S*stride <= (5920/rb + 1)(512 rb + 511), which the
+    // allocation below covers for the full system and for every row shard of it ...
     s->max_split = 256;
-    const size_t part_elems = (size_t)kPartComps * ((size_t)148 * 64 * 1024 + (size_t)std::max<int64_t>(s->nd_pad, round_up(nsite, 512)) + 1024);
+    // ... and a launch never has more splits than column tiles, which bounds small systems tightly
+    const size_t rows_pad = (size_t)std::max<int64_t>(s->nd_pad, round_up(nsite, 512));
+    const size_t tiles_max = (size_t)((s->na_pad + s->nb_pad) / kTileCols);
+    const size_t part_elems = (size_t)kPartComps * std::min<size_t>((size_t)148 * 64 * 1024 + rows_pad + 1024,
+                                                                    std::min<size_t>(tiles_max, 256) * rows_pad);
 
     int rc = UPOL_OK;
 #define TRY(x) do { rc = (x); if (rc) { free_system(s); return rc; } } while (0)
