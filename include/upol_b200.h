@@ -52,6 +52,7 @@ typedef struct upol_system upol_system;   /* one geometry + parameters resident 
 #define UPOL_FLAG_NOT_CONVERGED 1
 #define UPOL_FLAG_NONFINITE     2
 #define UPOL_FLAG_LINESEARCH    4
+#define UPOL_FLAG_COMM          8   /* a peer did not deliver within the time-out (P2P exchange) */
 
 /* layout of the energy vector written by the energy/gradient entry points (8 doubles) */
 #define UPOL_E_UIND    0   /* (U_coul - U_coul_static) + U_self      polarization.py:149       */
@@ -191,6 +192,18 @@ int upol_minimize_host(upol_system *sys, double *d, const upol_min_options *opts
 #define UPOL_COMM_ID_BYTES 128
 int upol_comm_unique_id(unsigned char *id_bytes);
 int upol_system_attach_comm(upol_system *sys, const unsigned char *id_bytes, int rank, int nranks);
+
+/*
+ * Peer-memory exchange for the minimiser loop (optional, after upol_system_attach_comm).  Each rank
+ * exports CUDA-IPC handles of its displacement vector, its scalar-pack mailbox and its arrival
+ * flags (UPOL_P2P_EXPORT_BYTES), the caller all-gathers the blobs (rank order) and hands them back.
+ * From then on a minimiser iteration uses no NCCL call: the update kernel stores its slice of d
+ * straight into every peer's vector over NVLink and raises the peers' arrival flags; the partial
+ * inner products travel the same way and every rank sums them in rank order (deterministic).
+ */
+#define UPOL_P2P_EXPORT_BYTES 192
+int upol_system_p2p_export(upol_system *sys, unsigned char *blob);
+int upol_system_p2p_attach(upol_system *sys, const unsigned char *all_blobs);
 
 /*
  * Batched independent small systems (SAPT-style dimer scan, replaces the subprocess-per-dimer

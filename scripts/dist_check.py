@@ -16,7 +16,7 @@ full = UindSystem.from_drude_system(s, device=lr)
 e1, g1 = full.energy_grad(D)
 d1, i1 = full.minimize(tol=1e-4)
 sh = UindSystem.from_drude_system(s, device=lr)
-sh.attach_process_group()
+sh.attach_process_group(p2p=os.environ.get("UPOL_NO_P2P") is None)
 e2, g2 = sh.energy_grad(D)
 torch.cuda.synchronize(); dist.barrier()
 t0 = time.perf_counter()

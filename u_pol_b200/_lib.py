@@ -16,6 +16,7 @@ FP64, MIXED = 0, 1
 LBFGS, CG = 0, 1
 FLAG_NOT_CONVERGED, FLAG_NONFINITE, FLAG_LINESEARCH = 1, 2, 4
 COMM_ID_BYTES = 128
+P2P_EXPORT_BYTES = 192
 
 
 class MinOptions(C.Structure):
@@ -58,6 +59,8 @@ _SIGNATURES = {
     "upol_minimize_host": (C.c_int, [_P, _P, C.POINTER(MinOptions), C.POINTER(MinResult)]),
     "upol_comm_unique_id": (C.c_int, [_P]),
     "upol_system_attach_comm": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "upol_system_p2p_export": (C.c_int, [_P, _P]),
+    "upol_system_p2p_attach": (C.c_int, [_P, _P]),
     "upol_batched_minimize_dev": (C.c_int, [C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P,
                                             C.c_double, C.c_int32, _P, _P, _P]),
     "upol_system_set_kernel_timing": (C.c_int, [_P, C.c_int]),

@@ -94,7 +94,18 @@ int comm_allgather_rows(upol_system *s, double *vec3, cudaStream_t st) {
     return a.GroupEnd() == ncclSuccess ? UPOL_OK : UPOL_ERR_NCCL;
 }
 
+void p2p_destroy(upol_system *s) {
+    for (void *p : s->ipc_opened) cudaIpcCloseMemHandle(p);
+    s->ipc_opened.clear();
+    void *ptrs[] = {s->xchg_pack, s->xchg_flags, s->d_peer_x, s->d_peer_pack, s->d_peer_flags};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    s->xchg_pack = nullptr; s->xchg_flags = nullptr;
+    s->d_peer_x = nullptr; s->d_peer_pack = nullptr; s->d_peer_flags = nullptr;
+    s->p2p = false;
+}
+
 void comm_destroy(upol_system *s) {
+    p2p_destroy(s);
     CommState *c = static_cast<CommState *>(s->comm);
     if (!c) return;
     if (c->comm && api().ok) api().CommDestroy(c->comm);
@@ -147,4 +158,61 @@ extern "C" int upol_system_attach_comm(upol_system *s, const unsigned char *id_b
     int64_t ml, mh;
     shard_bounds(s->nmol, nranks, rank, &ml, &mh);
     return upol_system_set_row_range(s, ml, mh);
+}
+
+// ---- peer-memory exchange (CUDA IPC over NVLink) -------------------------------------------------
+extern "C" int upol_system_p2p_export(upol_system *s, unsigned char *blob) {
+    if (!s || !blob || s->nranks < 2) return UPOL_ERR_ARG;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    p2p_destroy(s);
+    const size_t nflag = 2 * (size_t)s->nranks + 1;
+    cudaError_t e = cudaMalloc((void **)&s->xchg_pack, sizeof(double) * (size_t)s->nranks * kMaxPack);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->xchg_flags, sizeof(int) * nflag);
+    if (e == cudaSuccess) e = cudaMemset(s->xchg_pack, 0, sizeof(double) * (size_t)s->nranks * kMaxPack);
+    if (e == cudaSuccess) e = cudaMemset(s->xchg_flags, 0, sizeof(int) * nflag);
+    cudaIpcMemHandle_t h[3];
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[0], s->dc);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[1], s->xchg_pack);
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[2], s->xchg_flags);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (prev >= 0) cudaSetDevice(prev);
+    if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
+    static_assert(3 * sizeof(cudaIpcMemHandle_t) == UPOL_P2P_EXPORT_BYTES, "blob size");
+    memcpy(blob, h, sizeof(h));
+    s->p2p_epoch = 0;
+    return UPOL_OK;
+}
+
+extern "C" int upol_system_p2p_attach(upol_system *s, const unsigned char *all) {
+    if (!s || !all || s->nranks < 2 || !s->xchg_pack) return UPOL_ERR_ARG;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    const int nr = s->nranks;
+    std::vector<double *> px(nr), pp(nr);
+    std::vector<int *> pf(nr);
+    cudaError_t e = cudaSuccess;
+    for (int r = 0; r < nr && e == cudaSuccess; ++r) {
+        if (r == s->rank) { px[r] = s->dc; pp[r] = s->xchg_pack; pf[r] = s->xchg_flags; continue; }
+        cudaIpcMemHandle_t h[3];
+        memcpy(h, all + (size_t)r * UPOL_P2P_EXPORT_BYTES, sizeof(h));
+        void *q[3] = {nullptr, nullptr, nullptr};
+        for (int k = 0; k < 3 && e == cudaSuccess; ++k) {
+            e = cudaIpcOpenMemHandle(&q[k], h[k], cudaIpcMemLazyEnablePeerAccess);
+            if (e == cudaSuccess) s->ipc_opened.push_back(q[k]);
+        }
+        px[r] = (double *)q[0]; pp[r] = (double *)q[1]; pf[r] = (int *)q[2];
+    }
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_peer_x, sizeof(double *) * nr);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_peer_pack, sizeof(double *) * nr);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_peer_flags, sizeof(int *) * nr);
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_peer_x, px.data(), sizeof(double *) * nr, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_peer_pack, pp.data(), sizeof(double *) * nr, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_peer_flags, pf.data(), sizeof(int *) * nr, cudaMemcpyHostToDevice);
+    if (prev >= 0) cudaSetDevice(prev);
+    if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); p2p_destroy(s); return UPOL_ERR_CUDA; }
+    s->p2p = true;
+    return UPOL_OK;
 }

@@ -66,6 +66,7 @@ struct PairArgs {
 constexpr int kRowsMixed = 4;
 // gate bits written by the minimiser's control kernel
 constexpr int kGateDone = 1, kGatePhase64 = 2, kGatePhaseMixed = 4;
+constexpr int kMaxPack = 17 * 8;   // (max history + 1) x values per slot of the minimiser's scalar pack
 
 int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, cudaStream_t st);
 int launch_pair_mixed(const PairArgs &a, cudaStream_t st);
@@ -143,6 +144,17 @@ struct upol_system {
     void *comm = nullptr;
     int rank = 0, nranks = 1;
 
+    // peer-memory exchange of the minimiser (NVLink P2P through CUDA IPC, see comm.cu): every rank
+    // maps every other rank's displacement vector, scalar-pack mailbox and arrival flags
+    bool p2p = false;
+    double *xchg_pack = nullptr;      // [nranks][kMaxPack] mailbox: rank r's partial inner products
+    int *xchg_flags = nullptr;        // [2*nranks + 1] arrival epochs: packs, d slices; +1 block counter
+    double **d_peer_x = nullptr;      // device table [nranks]: peers' dc (self included)
+    double **d_peer_pack = nullptr;   // device table [nranks]: peers' xchg_pack
+    int **d_peer_flags = nullptr;     // device table [nranks]: peers' xchg_flags
+    std::vector<void *> ipc_opened;   // mapped peer pointers (closed at destroy)
+    int p2p_epoch = 0;                // last epoch handed out (monotonic across minimisations)
+
     // minimiser workspace (allocated on first use)
     void *min_ws = nullptr;
 
@@ -185,6 +197,7 @@ const char *last_error_message();
 int comm_allreduce_sum(upol_system *s, double *buf, int64_t n, cudaStream_t st);
 int comm_allgather_rows(upol_system *s, double *vec3, cudaStream_t st);  // [nd*3] in place by shard
 void comm_destroy(upol_system *s);
+void p2p_destroy(upol_system *s);
 
 // minimiser (minimize.cu)
 int minimize_compact(upol_system *s, double *d_compact, const upol_min_options *o,

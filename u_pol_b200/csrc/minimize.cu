@@ -175,6 +175,36 @@ precond_apply_kernel(int64_t e0, int64_t e1, const int *__restrict__ ic, const i
     Pg[e] = a; Py[e] = b;
 }
 
+// Peer-memory exchange (NVLink P2P, tables built by upol_system_p2p_attach).  epoch = id of the slot.
+struct P2P {
+    int on, rank, nranks, epoch;
+    double **peer_x;        // every rank's displacement vector
+    double **peer_pack;     // every rank's mailbox [nranks][kMaxPack]
+    int **peer_flags;       // every rank's arrival epochs [0,nranks): packs, [nranks,2nranks): d slices, [2nranks]: ticket
+    double *my_pack;        // this rank's mailbox
+    int *my_flags;
+};
+
+// Spin until flags[i] >= epoch (written by peer i through NVLink); ~2 s time-out instead of a hang.
+__device__ __forceinline__ bool wait_epoch(const int *flags, int i, int epoch) {
+    const volatile int *f = flags + i;
+    const long long t0 = clock64();
+    while (*f < epoch) {
+        if (clock64() - t0 > 4000000000LL) return false;
+        __nanosleep(200);
+    }
+    __threadfence_system();
+    return true;
+}
+
+// Before a field pass: all peers' slices of d (sent by their update kernels of the previous slot) are in.
+__global__ void wait_x_kernel(int *ic, P2P pp, int epoch_prev) {
+    if (ic[I_GATE] & kGateDone) return;
+    bool ok = true;
+    if ((int)threadIdx.x < pp.nranks && (int)threadIdx.x != pp.rank) ok = wait_epoch(pp.my_flags, pp.nranks + threadIdx.x, epoch_prev);
+    if (!__all_sync(0xffffffffu, ok) && threadIdx.x == 0) { ic[I_FLAGS] |= UPOL_FLAG_COMM; ic[I_GATE] |= kGateDone; }
+}
+
 __global__ void init_state_kernel(int *ic, double *sc, double tol, int phase_bits) {
     if (threadIdx.x || blockIdx.x) return;
     for (int i = 0; i < I_SIZE; ++i) ic[i] = 0;
@@ -228,23 +258,55 @@ dots_kernel(int m, int64_t n, int64_t e0, int64_t e1, const int *__restrict__ ic
     }
 }
 
-__global__ void dots_reduce_kernel(int m, int nblocks, const int *__restrict__ ic,
-                                   const double *__restrict__ partial, double *__restrict__ pack) {
+// One block.  Without peers: pack = sum of the block partials.  With peers: the local sums go into
+// every rank's mailbox slot of this rank over NVLink, then the arrival flag of this rank is raised on
+// every peer (fence, then flag); the controller below adds the mailboxes in rank order.
+__global__ void __launch_bounds__(kMaxPack + 24)
+dots_reduce_kernel(int m, int nblocks, const int *__restrict__ ic, const double *__restrict__ partial,
+                   double *__restrict__ pack, P2P pp) {
     if (ic[I_GATE] & kGateDone) return;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (m + 1) * kDotVals) return;
+    const int idx = threadIdx.x, len = (m + 1) * kDotVals;
     double t = 0.0;
-    if ((idx % kDotVals) < 6)
-        for (int b = 0; b < nblocks; ++b) t += partial[(int64_t)b * (m + 1) * kDotVals + idx];
-    pack[idx] = t;
+    if (idx < len && (idx % kDotVals) < 6)
+        for (int b = 0; b < nblocks; ++b) t += partial[(int64_t)b * len + idx];
+    if (!pp.on) {
+        if (idx < len) pack[idx] = t;
+        return;
+    }
+    if (idx < len)
+        for (int r = 0; r < pp.nranks; ++r) pp.peer_pack[r][(int64_t)pp.rank * kMaxPack + idx] = t;
+    __threadfence_system();
+    __syncthreads();
+    if (idx < pp.nranks) *((volatile int *)(pp.peer_flags[idx] + pp.rank)) = pp.epoch;
 }
 
 // Single-thread controller: line-search decision, history bookkeeping, m x m solves.
-__global__ void control_kernel(int m, int maxiter, int mixed_enabled, int *__restrict__ ic, double *__restrict__ sc,
-                               const double *__restrict__ pack, double *__restrict__ RS, double *__restrict__ YY,
-                               double *__restrict__ coef) {
-    if (threadIdx.x || blockIdx.x) return;
+__global__ void __launch_bounds__(kMaxPack + 24)
+control_kernel(int m, int maxiter, int mixed_enabled, int *__restrict__ ic, double *__restrict__ sc,
+               double *__restrict__ pack, double *__restrict__ RS, double *__restrict__ YY,
+               double *__restrict__ coef, P2P pp) {
     if (ic[I_GATE] & kGateDone) return;
+    if (pp.on) {
+        // wait for every rank's partial sums, then add them in rank order: every rank gets the same bits
+        __shared__ int bad;
+        if (threadIdx.x == 0) bad = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < pp.nranks && !wait_epoch(pp.my_flags, threadIdx.x, pp.epoch)) bad = 1;
+        __syncthreads();
+        if (bad) {
+            if (threadIdx.x == 0) { ic[I_FLAGS] |= UPOL_FLAG_COMM; ic[I_GATE] |= kGateDone; }
+            return;
+        }
+        const int len = (m + 1) * kDotVals;
+        if ((int)threadIdx.x < len) {
+            double t = 0.0;
+            for (int r = 0; r < pp.nranks; ++r) t += ((volatile double *)pp.my_pack)[(int64_t)r * kMaxPack + threadIdx.x];
+            pack[threadIdx.x] = t;
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    if (threadIdx.x) return;
     const double *last = pack + m * kDotVals;
     const double p_y = last[0], yPy = last[1], p_g = last[2], yPg = last[3], gg = last[4], gPg = last[5];
     ic[I_NEVAL] += 1;
@@ -400,11 +462,12 @@ update_kernel(int m, int64_t n, int64_t e0, int64_t e1, const int *__restrict__ 
               const double *__restrict__ coef, double *__restrict__ S, double *__restrict__ Y,
               double *__restrict__ x, double *__restrict__ x0, const double *__restrict__ g,
               double *__restrict__ g0, double *__restrict__ p, const double *__restrict__ Pg,
-              const double *__restrict__ Py) {
+              const double *__restrict__ Py, P2P pp) {
     if (ic[I_GATE] & kGateDone) return;
     const int64_t e = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= e1) return;
-    if (ic[I_ACCEPT]) {
+    const bool live = e < e1;
+    double xnew = 0.0;
+    if (live && ic[I_ACCEPT]) {
         const double ge = g[e];
         if (ic[I_PUSHED]) {
             const int ns = ic[I_NEWSLOT];
@@ -419,9 +482,28 @@ update_kernel(int m, int64_t n, int64_t e0, int64_t e1, const int *__restrict__ 
         }
         const double xe = x[e];
         x0[e] = xe; g0[e] = ge; p[e] = pn;
-        x[e] = xe + sc[D_ALPHA] * pn;
-    } else {
-        x[e] = x0[e] + sc[D_ALPHA] * p[e];
+        xnew = xe + sc[D_ALPHA] * pn;
+        x[e] = xnew;
+    } else if (live) {
+        xnew = x0[e] + sc[D_ALPHA] * p[e];
+        x[e] = xnew;
+    }
+    if (!pp.on) return;
+    // fused all-gather: this rank's slice goes straight into every peer's vector (NVLink stores) ...
+    if (live)
+        for (int r = 0; r < pp.nranks; ++r)
+            if (r != pp.rank) pp.peer_x[r][e] = xnew;
+    // ... and the block that finishes last raises this rank's arrival flag on every peer
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int last;
+    if (threadIdx.x == 0) last = (atomicAdd(pp.my_flags + 2 * pp.nranks, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) pp.my_flags[2 * pp.nranks] = 0;
+        __threadfence_system();
+        if ((int)threadIdx.x < pp.nranks && (int)threadIdx.x != pp.rank)
+            *((volatile int *)(pp.peer_flags[threadIdx.x] + pp.nranks + pp.rank)) = pp.epoch;
     }
 }
 
@@ -518,18 +600,31 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
     eo.gate = w->ic + I_GATE;
     eo.phase_switch = mixed;
 
+    P2P pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.on = (s->p2p && s->nranks > 1) ? 1 : 0;
+    pp.rank = s->rank; pp.nranks = s->nranks;
+    pp.peer_x = s->d_peer_x; pp.peer_pack = s->d_peer_pack; pp.peer_flags = s->d_peer_flags;
+    pp.my_pack = s->xchg_pack; pp.my_flags = s->xchg_flags;
+    int slots_in_call = 0;
+
     auto enqueue_slot = [&]() -> int {
+        if (pp.on) {
+            if (slots_in_call > 0) wait_x_kernel<<<1, 32, 0, st>>>(w->ic, pp, s->p2p_epoch);
+            pp.epoch = ++s->p2p_epoch;
+        }
+        ++slots_in_call;
         int r = sys_eval_compact(s, x, eo, s->energy, w->g, st);
         if (r) return r;
         dim3 dg((unsigned)w->nblocks, (unsigned)(m + 1));
         precond_apply_kernel<<<ublocks, 256, 0, st>>>(e0, e1, w->ic, w->row_mol, w->mol_row0, w->mol_nrow, w->blk_off,
                                                       w->blk, w->g, w->g0, w->Pg, w->Py);
         dots_kernel<<<dg, kDotBlock, 0, st>>>(m, n, e0, e1, w->ic, w->S, w->Y, w->g, w->g0, w->p, w->Pg, w->Py, w->partial);
-        dots_reduce_kernel<<<((m + 1) * kDotVals + 127) / 128, 128, 0, st>>>(m, w->nblocks, w->ic, w->partial, w->pack);
-        if (s->nranks > 1) { r = comm_allreduce_sum(s, w->pack, (int64_t)(m + 1) * kDotVals, st); if (r) return r; }
-        control_kernel<<<1, 1, 0, st>>>(m, o->maxiter, mixed ? 1 : 0, w->ic, w->sc, w->pack, w->RS, w->YY, w->coef);
-        update_kernel<<<ublocks, 256, 0, st>>>(m, n, e0, e1, w->ic, w->sc, w->coef, w->S, w->Y, x, w->x0, w->g, w->g0, w->p, w->Pg, w->Py);
-        if (s->nranks > 1) { r = comm_allgather_rows(s, x, st); if (r) return r; }
+        dots_reduce_kernel<<<1, kMaxPack + 24, 0, st>>>(m, w->nblocks, w->ic, w->partial, w->pack, pp);
+        if (s->nranks > 1 && !pp.on) { r = comm_allreduce_sum(s, w->pack, (int64_t)(m + 1) * kDotVals, st); if (r) return r; }
+        control_kernel<<<1, kMaxPack + 24, 0, st>>>(m, o->maxiter, mixed ? 1 : 0, w->ic, w->sc, w->pack, w->RS, w->YY, w->coef, pp);
+        update_kernel<<<ublocks, 256, 0, st>>>(m, n, e0, e1, w->ic, w->sc, w->coef, w->S, w->Y, x, w->x0, w->g, w->g0, w->p, w->Pg, w->Py, pp);
+        if (s->nranks > 1 && !pp.on) { r = comm_allgather_rows(s, x, st); if (r) return r; }
         UPOL_CUDA(cudaGetLastError());
         return UPOL_OK;
     };
@@ -557,6 +652,7 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
         }
         buf ^= 1;
     }
+    if (pp.on) wait_x_kernel<<<1, 32, 0, st>>>(w->ic, pp, s->p2p_epoch);   // only matters when not converged
     // fp64 energy at the minimiser (x is complete on every rank).  The gradient there is already
     // known from the last slot (its norm is in the control block), so this is a potential-only pass.
     EvalOpts ef;

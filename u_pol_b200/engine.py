@@ -206,10 +206,11 @@ class UindSystem:
         return ms.value, n.value
 
     # -- multi-GPU ------------------------------------------------------------------------
-    def attach_process_group(self, group=None):
+    def attach_process_group(self, group=None, p2p=True):
         """Row-shard this system over the ranks of a torch.distributed process group: creates the
         library's own NCCL communicator (id shipped with torch.distributed) and sets this rank's
-        molecule block."""
+        molecule block.  With ``p2p`` the minimiser loop then runs on peer-memory stores
+        (``enable_p2p``) and NCCL is used only for the energy/gradient entry points."""
         import torch.distributed as dist
 
         rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -223,6 +224,23 @@ class UindSystem:
             L.check(L.lib().upol_system_attach_comm(self._h, raw, rank, world), "upol_system_attach_comm")
         self.rank, self.nranks = rank, world
         self._mrange = shard_bounds(self.nmol, world, rank)
+        if p2p and world > 1:
+            self.enable_p2p(group)
+
+    def enable_p2p(self, group=None):
+        """Map every rank's displacement vector / mailbox / flags into every other rank (CUDA IPC over
+        NVLink) so that a minimiser iteration exchanges data with plain peer stores instead of NCCL."""
+        import torch.distributed as dist
+
+        blob = (C.c_ubyte * L.P2P_EXPORT_BYTES)()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().upol_system_p2p_export(self._h, blob), "upol_system_p2p_export")
+        blobs = [None] * dist.get_world_size(group)
+        dist.all_gather_object(blobs, bytes(blob), group=group)
+        allb = (C.c_ubyte * (L.P2P_EXPORT_BYTES * len(blobs))).from_buffer_copy(b"".join(blobs))
+        with torch.cuda.device(self.device):
+            L.check(L.lib().upol_system_p2p_attach(self._h, allb), "upol_system_p2p_attach")
+        dist.barrier(group)
 
     def set_row_range(self, mol_lo, mol_hi):
         L.check(L.lib().upol_system_set_row_range(self._h, int(mol_lo), int(mol_hi)))
