@@ -212,8 +212,10 @@ def run_cuda(args):
     n = s.nmol * s.natoms
     nd = int((s.q_shell != 0).sum())
     sysm = UindSystem.from_drude_system(s, device=local_rank)
+    exchange = "none"
     if world > 1:
         sysm.attach_process_group()
+        exchange = "peer-memory stores (CUDA IPC/NVLink) fused into the update kernel" if getattr(sysm, "p2p", False) else "nccl"
     d_dev = torch.as_tensor(d_host.reshape(-1)).to(dev)
     pairs_per_step = n * (n - 1)
     inter_local = sysm.interactions(False)
@@ -342,7 +344,8 @@ def run_cuda(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sites": n, "drudes": nd, "parallelism": f"row-shard x{world}",
                        "l2": "flushed between timed steps (256 MiB write, untimed)",
-                       "step": "full U_ind + grad incl. recomputed static part"},
+                       "step": "full U_ind + grad incl. recomputed static part",
+                       "minimiser_exchange": exchange},
             "interactions_per_s": (inter_local + inter_static_local) * world / (ms_per_step * 1e-3) if world == 1 else None,
             "U_ind": float(e_host[0]),
             "wall_s_timed_region": t_wall,

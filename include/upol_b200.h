@@ -204,6 +204,8 @@ int upol_system_attach_comm(upol_system *sys, const unsigned char *id_bytes, int
 #define UPOL_P2P_EXPORT_BYTES 192
 int upol_system_p2p_export(upol_system *sys, unsigned char *blob);
 int upol_system_p2p_attach(upol_system *sys, const unsigned char *all_blobs);
+/* Back to NCCL for the minimiser loop (every rank must call it, e.g. when a peer could not map). */
+int upol_system_p2p_disable(upol_system *sys);
 
 /*
  * Batched independent small systems (SAPT-style dimer scan, replaces the subprocess-per-dimer

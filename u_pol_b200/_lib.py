@@ -61,6 +61,7 @@ _SIGNATURES = {
     "upol_system_attach_comm": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "upol_system_p2p_export": (C.c_int, [_P, _P]),
     "upol_system_p2p_attach": (C.c_int, [_P, _P]),
+    "upol_system_p2p_disable": (C.c_int, [_P]),
     "upol_batched_minimize_dev": (C.c_int, [C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P,
                                             C.c_double, C.c_int32, _P, _P, _P]),
     "upol_system_set_kernel_timing": (C.c_int, [_P, C.c_int]),

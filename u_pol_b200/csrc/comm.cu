@@ -216,3 +216,14 @@ extern "C" int upol_system_p2p_attach(upol_system *s, const unsigned char *all) 
     s->p2p = true;
     return UPOL_OK;
 }
+
+extern "C" int upol_system_p2p_disable(upol_system *s) {
+    if (!s) return UPOL_ERR_ARG;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    p2p_destroy(s);
+    if (prev >= 0) cudaSetDevice(prev);
+    return UPOL_OK;
+}

@@ -234,13 +234,22 @@ class UindSystem:
 
         blob = (C.c_ubyte * L.P2P_EXPORT_BYTES)()
         with torch.cuda.device(self.device):
-            L.check(L.lib().upol_system_p2p_export(self._h, blob), "upol_system_p2p_export")
-        blobs = [None] * dist.get_world_size(group)
-        dist.all_gather_object(blobs, bytes(blob), group=group)
-        allb = (C.c_ubyte * (L.P2P_EXPORT_BYTES * len(blobs))).from_buffer_copy(b"".join(blobs))
-        with torch.cuda.device(self.device):
-            L.check(L.lib().upol_system_p2p_attach(self._h, allb), "upol_system_p2p_attach")
+            ok = L.lib().upol_system_p2p_export(self._h, blob) == 0
+        got = [None] * dist.get_world_size(group)
+        dist.all_gather_object(got, (ok, bytes(blob)), group=group)
+        ok = all(g[0] for g in got)
+        if ok:
+            allb = (C.c_ubyte * (L.P2P_EXPORT_BYTES * len(got))).from_buffer_copy(b"".join(g[1] for g in got))
+            with torch.cuda.device(self.device):
+                ok = L.lib().upol_system_p2p_attach(self._h, allb) == 0
+        agree = [None] * dist.get_world_size(group)
+        dist.all_gather_object(agree, ok, group=group)
+        if not all(agree):                      # some rank could not map its peers: everyone stays on NCCL
+            with torch.cuda.device(self.device):
+                L.lib().upol_system_p2p_disable(self._h)
+        self.p2p = all(agree)
         dist.barrier(group)
+        return self.p2p
 
     def set_row_range(self, mol_lo, mol_hi):
         L.check(L.lib().upol_system_set_row_range(self._h, int(mol_lo), int(mol_hi)))
