@@ -220,6 +220,9 @@ def run_cuda(args):
     pairs_per_step = n * (n - 1)
     inter_local = sysm.interactions(False)
     inter_static_local = sysm.interactions(True)
+    n_d_mol = int((s.q_shell[0] != 0).sum())
+    inter_total = s.nmol * n_d_mol * ((n - s.natoms) + (nd - n_d_mol))          # I_inter, SURVEY 8d
+    inter_static_total = s.nmol * n_d_mol * (n - s.natoms)
 
     def barrier():
         torch.cuda.synchronize()
@@ -346,7 +349,7 @@ def run_cuda(args):
                        "l2": "flushed between timed steps (256 MiB write, untimed)",
                        "step": "full U_ind + grad incl. recomputed static part",
                        "minimiser_exchange": exchange},
-            "interactions_per_s": (inter_local + inter_static_local) * world / (ms_per_step * 1e-3) if world == 1 else None,
+            "interactions_per_s": (inter_total + inter_static_total) / (ms_per_step * 1e-3),
             "U_ind": float(e_host[0]),
             "wall_s_timed_region": t_wall,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
