@@ -127,7 +127,8 @@ int upol_uind_energy_grad_host(upol_system *sys, const double *d, int precision,
 /*
  * dUind/dr_core at fixed displacements, dudr[nsite*3] (kJ mol^-1 nm^-1); the force on core i is
  * -dudr[i].  NEW relative to the reference (SURVEY 8f "next" #3): U_pol has no such function; it
- * is what an MD driver needs to move the cores on the U_ind surface.  fp64; single rank.
+ * is what an MD driver needs to move the cores on the U_ind surface.  fp64.  Sharded runs compute the
+ * sites of the rank's molecule block and all-gather the result.
  */
 int upol_uind_core_gradient_dev(upol_system *sys, const double *d, double *dudr, void *stream);
 

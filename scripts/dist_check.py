@@ -30,4 +30,17 @@ dd = float((d2 - d1).abs().max())
 print(f"rank {rank}/{world}: dE {rel_e:.2e} dg {rel_g:.2e} dUmin {rel_m:.2e} dd {dd:.2e} iters {i1['iterations']}/{i2['iterations']} "
       f"evals {i1['evaluations']}/{i2['evaluations']} t_full {t_full:.3f}s t_sharded {t_sh:.3f}s", flush=True)
 assert rel_e < 1e-11 and rel_g < 1e-12 and rel_m < 1e-10, "sharded result differs"
+cg1 = full.core_gradient(D); cg2 = sh.core_gradient(D)
+rel_c = float((cg1 - cg2).abs().max() / cg1.abs().max())
+assert rel_c < 1e-12, rel_c
+print(f"rank {rank}: sharded core gradient ok ({rel_c:.1e})", flush=True)
+# config 5: replicas only
+from u_pol_b200.engine import batched_minimize, batched_minimize_replicas
+z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "dimers312.npz"))
+al, qs = z["alpha"], z["q_shell"]
+kk = np.where(al == 0, 0.0, 138.93545764438198 * qs**2 / np.where(al == 0, 1.0, al))
+dA, eA, itA = batched_minimize_replicas(z["r_core"], z["q_core"], qs, kk, z["thole_u"], tol=1e-6)
+dB, eB, itB = batched_minimize(z["r_core"], z["q_core"], qs, kk, z["thole_u"], tol=1e-6)
+assert torch.equal(eA[:, 0], eB[:, 0]) and torch.equal(itA, itB) and eA.shape[0] == 312
+print(f"rank {rank}: batched replicas ok ({eA.shape[0]} systems)", flush=True)
 dist.barrier(); dist.destroy_process_group()

@@ -19,4 +19,4 @@ def test_two_rank_nccl_matches_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "scripts", "dist_check.py"), "1000"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("rank ") == 2
+    assert out.stdout.count("dE ") == 2 and out.stdout.count("batched replicas ok") == 2 and out.stdout.count("sharded core gradient ok") == 2

@@ -65,6 +65,7 @@ NcclApi &api() {
 struct CommState {
     ncclComm_t comm = nullptr;
     std::vector<int64_t> row_lo, row_hi;   // Drude-row range of every rank
+    std::vector<int64_t> site_lo, site_hi; // site range of every rank
 };
 
 }  // namespace
@@ -89,6 +90,21 @@ int comm_allgather_rows(upol_system *s, double *vec3, cudaStream_t st) {
         const int64_t n = 3 * (c->row_hi[g] - c->row_lo[g]);
         if (n <= 0) continue;
         double *p = vec3 + 3 * c->row_lo[g];
+        if (a.Broadcast(p, p, (size_t)n, ncclFloat64, g, c->comm, st) != ncclSuccess) { a.GroupEnd(); return UPOL_ERR_NCCL; }
+    }
+    return a.GroupEnd() == ncclSuccess ? UPOL_OK : UPOL_ERR_NCCL;
+}
+
+int comm_allgather_sites(upol_system *s, double *vec3, cudaStream_t st) {
+    if (s->nranks <= 1) return UPOL_OK;
+    CommState *c = static_cast<CommState *>(s->comm);
+    if (!c || !api().ok) return UPOL_ERR_NCCL;
+    NcclApi &a = api();
+    if (a.GroupStart() != ncclSuccess) return UPOL_ERR_NCCL;
+    for (int g = 0; g < s->nranks; ++g) {
+        const int64_t n = 3 * (c->site_hi[g] - c->site_lo[g]);
+        if (n <= 0) continue;
+        double *p = vec3 + 3 * c->site_lo[g];
         if (a.Broadcast(p, p, (size_t)n, ncclFloat64, g, c->comm, st) != ncclSuccess) { a.GroupEnd(); return UPOL_ERR_NCCL; }
     }
     return a.GroupEnd() == ncclSuccess ? UPOL_OK : UPOL_ERR_NCCL;
@@ -148,11 +164,14 @@ extern "C" int upol_system_attach_comm(upol_system *s, const unsigned char *id_b
     if (prev >= 0) cudaSetDevice(prev);
     if (rc != ncclSuccess) { delete c; return UPOL_ERR_NCCL; }
     c->row_lo.resize(nranks); c->row_hi.resize(nranks);
+    c->site_lo.resize(nranks); c->site_hi.resize(nranks);
     for (int g = 0; g < nranks; ++g) {
         int64_t ml, mh;
         shard_bounds(s->nmol, nranks, g, &ml, &mh);
         c->row_lo[g] = ml < s->nmol ? s->h_mol_row0[ml] : s->nd;
         c->row_hi[g] = mh < s->nmol ? s->h_mol_row0[mh] : s->nd;
+        c->site_lo[g] = ml < s->nmol ? s->h_mol_site0[ml] : s->nsite;
+        c->site_hi[g] = mh < s->nmol ? s->h_mol_site0[mh] : s->nsite;
     }
     s->comm = c; s->rank = rank; s->nranks = nranks;
     int64_t ml, mh;

@@ -196,6 +196,7 @@ const char *last_error_message();
 // collectives (comm.cu)
 int comm_allreduce_sum(upol_system *s, double *buf, int64_t n, cudaStream_t st);
 int comm_allgather_rows(upol_system *s, double *vec3, cudaStream_t st);  // [nd*3] in place by shard
+int comm_allgather_sites(upol_system *s, double *vec3, cudaStream_t st); // [nsite*3] in place by shard
 void comm_destroy(upol_system *s);
 void p2p_destroy(upol_system *s);
 

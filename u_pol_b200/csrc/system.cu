@@ -622,8 +622,8 @@ int sys_coulomb_static(upol_system *s, double *out2, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------
 template <int NC>
 __global__ void __launch_bounds__(kFinBlock)
-fold_fields_kernel(int n_rows, int n_split, const double *__restrict__ part, int64_t stride, int c0,
-                   double *__restrict__ dst) {
+fold_fields_kernel(int n_rows, int row0, int64_t dst_stride, int n_split, const double *__restrict__ part,
+                   int64_t stride, int c0, double *__restrict__ dst) {
     __shared__ double fold[kFinLanes][kFinRows][kPartComps];
     const int lr = blockIdx.x * kFinRows + threadIdx.x % kFinRows;
     const bool live = lr < n_rows;
@@ -631,7 +631,7 @@ fold_fields_kernel(int n_rows, int n_split, const double *__restrict__ part, int
     fold_splits<NC>(part, stride, lr, live, n_split, c0, fold, v);
     if (live && threadIdx.x < kFinRows) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) dst[(int64_t)c * n_rows + lr] = v[c];
+        for (int c = 0; c < NC; ++c) dst[(int64_t)c * dst_stride + row0 + lr] = v[c];
     }
 }
 
@@ -647,15 +647,15 @@ __global__ void build_force_tables_kernel(int nsite, int nd, int nb_pad, const d
     }
 }
 
-__global__ void core_force_assemble_kernel(int nsite, int nd, const double *__restrict__ r, const double *__restrict__ dc,
+__global__ void core_force_assemble_kernel(int site_lo, int site_hi, int nsite, int nd, const double *__restrict__ r, const double *__restrict__ dc,
                                            const double *__restrict__ qc, const double *__restrict__ qs,
                                            const int *__restrict__ site_row, const int *__restrict__ row_site,
                                            const double *__restrict__ row_qs, const int *__restrict__ th_ptr,
                                            const int *__restrict__ th_row, const double *__restrict__ th_u,
                                            const double *__restrict__ F, const double *__restrict__ H,
                                            const double *__restrict__ GH, double *__restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nsite) return;
+    const int j = site_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= site_hi) return;
     const double qe = qc[j] + 0.5 * qs[j];
     double g[3];
     for (int c = 0; c < 3; ++c) g[c] = kCoulomb * (qc[j] * GH[(int64_t)c * nsite + j] - qe * GH[(int64_t)(3 + c) * nsite + j]);
@@ -685,7 +685,6 @@ __global__ void core_force_assemble_kernel(int nsite, int nd, const double *__re
 }
 
 int sys_core_forces(upol_system *s, const double *dcmp, double *dudr, cudaStream_t st) {
-    if (s->nranks > 1) return UPOL_ERR_ARG;     // single-rank for now (columns and rows are all local)
     const int64_t n = s->nsite, nd = s->nd;
     if (!s->cf_tmp) {      // first use: tables of the site-row pass
         s->ns_pad = round_up(n, 512);
@@ -705,49 +704,56 @@ int sys_core_forces(upol_system *s, const double *dcmp, double *dudr, cudaStream
     }
     UPOL_CUDA(cudaMemsetAsync(dudr, 0, sizeof(double) * 3 * n, st));
     if (nd == 0) return UPOL_OK;
+    // this rank's share: Drude rows and sites of its molecule block (all of them on a single rank)
+    const int64_t r_lo = s->row_lo, nr = s->row_hi - s->row_lo;
+    const int64_t s_lo = s->mol_lo < s->nmol ? s->h_mol_site0[s->mol_lo] : n;
+    const int64_t s_hi = s->mol_hi < s->nmol ? s->h_mol_site0[s->mol_hi] : n;
+    const int64_t ns = s_hi - s_lo;
     double *F = s->cf_tmp, *H = F + 3 * nd, *GH = H + 3 * nd;
     prepare_shells_kernel<<<nblk(s->nb_pad, 256), 256, 0, st>>>(
         (int)nd, (int)s->nb_pad, s->row_site, s->r, dcmp, s->row_qs, s->centre[0], s->centre[1], s->centre[2],
         s->inv_grid, s->mix_slot, s->rowx, s->rowy, s->rowz, s->cols + s->na_pad, s->cols_f);
     build_force_tables_kernel<<<nblk(std::max<int64_t>(n, s->nb_pad), 256), 256, 0, st>>>(
         (int)n, (int)nd, (int)s->nb_pad, s->r, s->row_site, s->row_qs, s->site_x, s->site_y, s->site_z, s->cols_dcore);
-    const int nbf = (int)nblk(nd, kFinRows);
-    {   // F: field at the shells (main pass, field only)
-        PairArgs a = base_args(s);
-        a.n_rows = (int)nd; a.row0 = 0; a.part_stride = part_stride_for(nd);
-        a.rx = s->rowx; a.ry = s->rowy; a.rz = s->rowz;
-        a.cols = s->cols; a.n_tiles = (int)((s->na_pad + s->nb_pad) / kTileCols);
-        a.n_split = choose_split(s, nd, a.n_tiles, fp64_rows_per_block());
-        int rc = launch_pair_fp64(a, false, true, st);
-        if (rc) return rc;
-        fold_fields_kernel<3><<<nbf, kFinBlock, 0, st>>>((int)nd, a.n_split, s->part, a.part_stride, 2, F);
+    if (nr > 0) {
+        const int nbf = (int)nblk(nr, kFinRows);
+        {   // F: field at the shells (main pass, field only)
+            PairArgs a = base_args(s);
+            a.rx = s->rowx; a.ry = s->rowy; a.rz = s->rowz;
+            a.cols = s->cols; a.n_tiles = (int)((s->na_pad + s->nb_pad) / kTileCols);
+            a.n_split = choose_split(s, nr, a.n_tiles, fp64_rows_per_block());
+            int rc = launch_pair_fp64(a, false, true, st);
+            if (rc) return rc;
+            fold_fields_kernel<3><<<nbf, kFinBlock, 0, st>>>((int)nr, (int)r_lo, nd, a.n_split, s->part, a.part_stride, 2, F);
+        }
+        {   // H: field at the Drude cores from the static charges
+            PairArgs a = base_args(s);
+            a.rx = s->srowx; a.ry = s->srowy; a.rz = s->srowz;
+            a.cols = s->cols_static; a.n_tiles = a.n_tiles_a;
+            a.n_split = choose_split(s, nr, a.n_tiles, fp64_rows_per_block());
+            int rc = launch_pair_fp64(a, false, true, st);
+            if (rc) return rc;
+            fold_fields_kernel<3><<<nbf, kFinBlock, 0, st>>>((int)nr, (int)r_lo, nd, a.n_split, s->part, a.part_stride, 2, H);
+        }
     }
-    {   // H: field at the Drude cores from the static charges
+    if (ns > 0) {   // G, H': fields at every core of the block from the other molecules' shells / Drude cores
         PairArgs a = base_args(s);
-        a.n_rows = (int)nd; a.row0 = 0; a.part_stride = part_stride_for(nd);
-        a.rx = s->srowx; a.ry = s->srowy; a.rz = s->srowz;
-        a.cols = s->cols_static; a.n_tiles = a.n_tiles_a;
-        a.n_split = choose_split(s, nd, a.n_tiles, fp64_rows_per_block());
-        int rc = launch_pair_fp64(a, false, true, st);
-        if (rc) return rc;
-        fold_fields_kernel<3><<<nbf, kFinBlock, 0, st>>>((int)nd, a.n_split, s->part, a.part_stride, 2, H);
-    }
-    {   // G, H': fields at every core from the other molecules' shells / Drude cores
-        PairArgs a = base_args(s);
-        a.n_rows = (int)n; a.row0 = 0; a.part_stride = part_stride_for(n);
+        a.n_rows = (int)ns; a.row0 = (int)s_lo; a.part_stride = part_stride_for(ns);
         a.rx = s->site_x; a.ry = s->site_y; a.rz = s->site_z;
         a.exA_lo = s->exS_lo; a.exA_len = s->exS_len; a.exB_lo = s->exS2_lo; a.exB_len = s->exS_len;
         a.cols = s->cols + s->na_pad;           // shells (refreshed by prepare_shells above)
         a.cols_b = s->cols_dcore;
         a.n_tiles_a = (int)(s->nb_pad / kTileCols); a.n_tiles = 2 * a.n_tiles_a;
-        a.n_split = choose_split(s, n, a.n_tiles, fp64_rows_per_block());
+        a.n_split = choose_split(s, ns, a.n_tiles, fp64_rows_per_block());
         int rc = launch_pair_fp64_two_fields(a, st);
         if (rc) return rc;
-        fold_fields_kernel<6><<<nblk(n, kFinRows), kFinBlock, 0, st>>>((int)n, a.n_split, s->part, a.part_stride, 0, GH);
+        fold_fields_kernel<6><<<nblk(ns, kFinRows), kFinBlock, 0, st>>>((int)ns, (int)s_lo, n, a.n_split, s->part, a.part_stride, 0, GH);
+        core_force_assemble_kernel<<<nblk(ns, 128), 128, 0, st>>>((int)s_lo, (int)s_hi, (int)n, (int)nd, s->r, dcmp, s->qc, s->qs,
+                                                                 s->site_row, s->row_site, s->row_qs, s->th_ptr, s->th_row,
+                                                                 s->th_u, F, H, GH, dudr);
     }
-    core_force_assemble_kernel<<<nblk(n, 128), 128, 0, st>>>((int)n, (int)nd, s->r, dcmp, s->qc, s->qs, s->site_row,
-                                                             s->row_site, s->row_qs, s->th_ptr, s->th_row, s->th_u, F, H, GH, dudr);
     UPOL_CUDA(cudaGetLastError());
+    if (s->nranks > 1) return comm_allgather_sites(s, dudr, st);
     return UPOL_OK;
 }
 

@@ -304,3 +304,26 @@ def batched_minimize(r_batch, q_core, q_shell, k, thole_u=None, d0=None, tol=1e-
             e.data_ptr(), it.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
             "upol_batched_minimize_dev")
     return d.reshape(B, nsite, 3), e, it
+
+
+def batched_minimize_replicas(r_batch, q_core, q_shell, k, thole_u=None, tol=1e-4, maxiter=500, group=None):
+    """BASELINE config 5 on several GPUs: independent systems need no data-path collective ("replicas
+    only") - every rank minimises its contiguous share of the batch on its own GPU and the
+    results are all-gathered for convenience.  Returns (d_opt, energy, iterations) for the WHOLE batch on
+    every rank (CUDA tensors on the rank's device)."""
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    r = torch.as_tensor(r_batch, dtype=torch.float64) if not isinstance(r_batch, torch.Tensor) else r_batch
+    B = int(r.shape[0])
+    lo, hi = B * rank // world, B * (rank + 1) // world
+    d, e, it = batched_minimize(r[lo:hi], q_core, q_shell, k, thole_u, tol=tol, maxiter=maxiter)
+    dev = d.device
+    per = (B + world - 1) // world
+    pad = lambda t: torch.cat([t, torch.zeros((per - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)])
+    outs = []
+    for t in (d, e, it):
+        bufs = [torch.empty((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for _ in range(world)]
+        dist.all_gather(bufs, pad(t), group=group)
+        outs.append(torch.cat([bufs[g][: B * (g + 1) // world - B * g // world] for g in range(world)]))
+    return tuple(outs)
