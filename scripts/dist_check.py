@@ -32,7 +32,7 @@ print(f"rank {rank}/{world}: dE {rel_e:.2e} dg {rel_g:.2e} dUmin {rel_m:.2e} dd 
 assert rel_e < 1e-11 and rel_g < 1e-12 and rel_m < 1e-10, "sharded result differs"
 cg1 = full.core_gradient(D); cg2 = sh.core_gradient(D)
 rel_c = float((cg1 - cg2).abs().max() / cg1.abs().max())
-assert rel_c < 1e-12, rel_c
+assert rel_c < 1e-10, rel_c
 print(f"rank {rank}: sharded core gradient ok ({rel_c:.1e})", flush=True)
 # config 5: replicas only
 from u_pol_b200.engine import batched_minimize, batched_minimize_replicas

@@ -77,37 +77,43 @@ int comm_allreduce_sum(upol_system *s, double *buf, int64_t n, cudaStream_t st) 
     return api().AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, c->comm, st) == ncclSuccess ? UPOL_OK : UPOL_ERR_NCCL;
 }
 
+// In-place gather of per-rank slices [lo[g], hi[g]) * 3 doubles.  Equal slices -> one ncclAllGather
+// (in place: every rank's send buffer is its own slice of the receive buffer); uneven slices (molecule
+// blocks differ by one molecule) -> a group of broadcasts, which NCCL fuses into one launch.
+static int gather_slices(upol_system *s, CommState *c, const std::vector<int64_t> &lo, const std::vector<int64_t> &hi,
+                         double *vec3, cudaStream_t st) {
+    NcclApi &a = api();
+    bool equal = true;
+    const int64_t n0 = hi[0] - lo[0];
+    for (int g = 0; g < s->nranks; ++g) equal = equal && (hi[g] - lo[g] == n0) && (lo[g] == lo[0] + g * n0);
+    if (equal && n0 > 0) {
+        double *base = vec3 + 3 * lo[0];
+        return a.AllGather(base + 3 * n0 * s->rank, base, (size_t)(3 * n0), ncclFloat64, c->comm, st) == ncclSuccess
+                   ? UPOL_OK : UPOL_ERR_NCCL;
+    }
+    if (a.GroupStart() != ncclSuccess) return UPOL_ERR_NCCL;
+    for (int g = 0; g < s->nranks; ++g) {
+        const int64_t n = 3 * (hi[g] - lo[g]);
+        if (n <= 0) continue;
+        double *p = vec3 + 3 * lo[g];
+        if (a.Broadcast(p, p, (size_t)n, ncclFloat64, g, c->comm, st) != ncclSuccess) { a.GroupEnd(); return UPOL_ERR_NCCL; }
+    }
+    return a.GroupEnd() == ncclSuccess ? UPOL_OK : UPOL_ERR_NCCL;
+}
+
 // All-gather of a row-sliced [nd*3] vector, in place: rank g owns rows [row_lo[g], row_hi[g]).
-// Shards are whole molecules and may differ in size by one molecule, so the gather is a group
-// of broadcasts (NCCL fuses a group into one launch).
 int comm_allgather_rows(upol_system *s, double *vec3, cudaStream_t st) {
     if (s->nranks <= 1) return UPOL_OK;
     CommState *c = static_cast<CommState *>(s->comm);
     if (!c || !api().ok) return UPOL_ERR_NCCL;
-    NcclApi &a = api();
-    if (a.GroupStart() != ncclSuccess) return UPOL_ERR_NCCL;
-    for (int g = 0; g < s->nranks; ++g) {
-        const int64_t n = 3 * (c->row_hi[g] - c->row_lo[g]);
-        if (n <= 0) continue;
-        double *p = vec3 + 3 * c->row_lo[g];
-        if (a.Broadcast(p, p, (size_t)n, ncclFloat64, g, c->comm, st) != ncclSuccess) { a.GroupEnd(); return UPOL_ERR_NCCL; }
-    }
-    return a.GroupEnd() == ncclSuccess ? UPOL_OK : UPOL_ERR_NCCL;
+    return gather_slices(s, c, c->row_lo, c->row_hi, vec3, st);
 }
 
 int comm_allgather_sites(upol_system *s, double *vec3, cudaStream_t st) {
     if (s->nranks <= 1) return UPOL_OK;
     CommState *c = static_cast<CommState *>(s->comm);
     if (!c || !api().ok) return UPOL_ERR_NCCL;
-    NcclApi &a = api();
-    if (a.GroupStart() != ncclSuccess) return UPOL_ERR_NCCL;
-    for (int g = 0; g < s->nranks; ++g) {
-        const int64_t n = 3 * (c->site_hi[g] - c->site_lo[g]);
-        if (n <= 0) continue;
-        double *p = vec3 + 3 * c->site_lo[g];
-        if (a.Broadcast(p, p, (size_t)n, ncclFloat64, g, c->comm, st) != ncclSuccess) { a.GroupEnd(); return UPOL_ERR_NCCL; }
-    }
-    return a.GroupEnd() == ncclSuccess ? UPOL_OK : UPOL_ERR_NCCL;
+    return gather_slices(s, c, c->site_lo, c->site_hi, vec3, st);
 }
 
 void p2p_destroy(upol_system *s) {
