@@ -117,7 +117,10 @@ int upol_system_set_row_range(upol_system *sys, int64_t mol_lo, int64_t mol_hi);
  *   grad[nsite*3]        may be NULL (energy only)
  * precision selects the arithmetic of the FIELD (gradient).  The potential (energy) is always
  * accumulated from fp64 pair terms: U_ind is the small difference U_coul - U_coul_static of two
- * large sums and fp32 pair terms cannot deliver it to 1e-5 ("mixed mode").
+ * large sums and fp32 pair terms cannot deliver it to 1e-5 ("mixed mode").  When the
+ * energy is requested as well, the fp64 kernel produces the field in the same pass (cheaper than an
+ * extra fp32 pass), so UPOL_MIXED changes the arithmetic of field-only calls (energy == NULL) and of
+ * the minimiser's iterations.
  */
 int upol_uind_energy_grad_dev(upol_system *sys, const double *d, int precision,
                               double *energy, double *grad, void *stream);

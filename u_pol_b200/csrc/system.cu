@@ -368,8 +368,13 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
         const int split64 = choose_split(s, a.n_rows, a.n_tiles, fp64_rows_per_block());
         const int splitmx = choose_split(s, a.n_rows, a.n_tiles, kBlock * kRowsMixed);
         int split_pot = 0, split_f64 = 0, split_mx = 0;
-        const bool f64_field = o.want_grad && (o.precision == UPOL_FP64 || o.phase_switch);
-        const bool mx_field = o.want_grad && o.precision == UPOL_MIXED;
+        // The potential always needs the fp64 kernel, and that kernel delivers the field in the same pass
+        // for 1.5x the time of the potential alone - cheaper than adding a separate fp32 field pass.  So a
+        // mixed-precision call that also asks for the energy gets the fp64 field; the fp32 field kernel
+        // serves field-only calls (what a minimiser iteration is).
+        const bool mixed_field_only = o.precision == UPOL_MIXED && (!o.want_energy || o.phase_switch);
+        const bool f64_field = o.want_grad && (!mixed_field_only || o.phase_switch);
+        const bool mx_field = o.want_grad && mixed_field_only;
         int rc = UPOL_OK;
         if (f64_field || o.want_energy) {
             // fp64 kernel: potential and/or field.  With a mixed field the fp64 launch carries the
