@@ -61,3 +61,20 @@ def test_long_double_arbiter_agrees_with_both_oracles():
     Dw = synth.random_displacements(w, seed=14)
     ew, _ = c_oracle.energy_grad(w.r_core, Dw, w.q_core, w.q_shell, w.k, None, want_grad=False)
     assert ew[0] == pytest.approx(c_oracle.uind_long_double(w.r_core, Dw, w.q_core, w.q_shell, w.k, None), rel=1e-11)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_c_oracle_vs_dense_random_topologies(seed):
+    """Same random-topology generator as the GPU suite: the two CPU oracles agree on every draw."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "_rt", os.path.join(os.path.dirname(__file__), "test_gpu_random_topologies.py"))
+    rt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rt)
+    r, qc, qs, k, th, D = rt._random_system(1000 + seed)
+    Rij, qis, qjs, qic, qjc, u, kk = O.dense_inputs(r, qc, qs, k, th)
+    e_ref, g_ref = O.u_ind_and_grad(Rij, D, qis, qjs, qic, qjc, u, kk)
+    e, g = c_oracle.energy_grad(r, D, qc, qs, k, th)
+    assert abs(e[0] - e_ref) <= 1e-11 * abs(e_ref) + 1e-14 * (abs(e[1]) + abs(e[2]))
+    assert np.abs(g - g_ref).max() <= 1e-11 * max(np.abs(g_ref).max(), 1e-9)
