@@ -75,3 +75,26 @@ def test_product_does_not_import_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "uind_oracle" not in src, f
+
+
+def test_header_is_valid_c_and_plain_c_program_links(tmp_path):
+    """include/upol_b200.h is a C header (not only C++): a C99 program that uses it compiles with
+    -Wall -Werror, links against the shared library and runs (without a GPU it stops after the
+    constant, as the library has no CPU fallback)."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "c_api_example")
+    libdir = os.path.dirname(L.LIB_PATH)
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_api_example.c"), "-L", libdir, "-lupol_b200",
+           f"-Wl,-rpath,{libdir}", "-o", exe]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "ONE_4PI_EPS0 = 138.93545764438" in run.stdout
+    if torch.cuda.is_available():
+        assert "minimised U_ind = -" in run.stdout

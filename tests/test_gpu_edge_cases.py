@@ -158,3 +158,35 @@ def test_host_buffer_minimise_and_device_positions():
     g64 = sys_.energy_grad(D)[1]
     gmx = sys_.energy_grad(D, precision="mixed", want_energy=False)[1]
     assert float((gmx - g64).abs().max()) <= 1e-5 * float(g64.abs().max())
+
+
+def test_plain_c_program_through_the_c_abi(tmp_path):
+    """examples/c_api_example.c: a C99 program (no Python, no torch) creates a system, evaluates and
+    minimises through the host-buffer entry points."""
+    import os
+    import shutil
+    import subprocess
+    from u_pol_b200 import _lib as L
+
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "c_api_example")
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "c_api_example.c"), "-L", libdir, "-lupol_b200",
+                    f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    line = [l for l in run.stdout.splitlines() if l.startswith("minimised U_ind")][0]
+    u = float(line.split("=")[1].split()[0])
+    # same system through the Python mirror
+    K = 138.93545764438198
+    r = np.array([[0.0, 0.0, 0.0], [0.0757, 0.0, 0.0586], [-0.0757, 0.0, 0.0586], [0.0, 0.0, 0.0240],
+                  [0.30, 0.0, 0.0], [0.3757, 0.0, 0.0586], [0.2243, 0.0, 0.0586], [0.30, 0.0, 0.0240]]).reshape(2, 4, 3)
+    qc = np.tile([1.71636, 0.55733, 0.55733, -1.11466], (2, 1))
+    qs = np.tile([-1.71636, 0.0, 0.0, 0.0], (2, 1))
+    k = np.where(qs != 0, K * qs**2 / 0.000978253, 0.0)
+    _, info = UindSystem.from_compact(r, qc, qs, k, None).minimize(tol=1e-4)
+    assert u == pytest.approx(info["U_ind"], rel=1e-8) and u < 0
