@@ -28,6 +28,12 @@
 
 namespace upol {
 
+// High word of 1e-10 (nm^2): squared distances below it (r < 1e-5 nm, five orders of magnitude below any
+// physical contact) are treated as the reference's zero distance, whose term is dropped
+// (polarization.py:33-42).  One threshold for the direct and the expanded-square kernels; the latter
+// cannot tell an exact zero from its ~1e-14 cancellation noise.
+constexpr int kZeroR2Hi = 0x3DDB7CDF;
+
 // Compensated accumulation (Knuth two-sum) of a tile partial into a (hi, lo) pair.  The row
 // potentials reach ~2e4 e/nm at 100 k Drudes (all core charges positive, all shells negative) while
 // U_ind is their ~1e-6 remainder; adding 128-column tile partials (~10) into such an accumulator
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
                     }
                 }
             }
-            careful = __any_sync(0xffffffffu, hmin < 0x00100000);      // zero or subnormal r^2
+            careful = __any_sync(0xffffffffu, hmin < kZeroR2Hi);       // r < 1e-5 nm counts as zero distance
             if (careful) {
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) ph[r] = tx[r] = ty[r] = tz[r] = 0.0;
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
                 for (int r = 0; r < ROWS; ++r) {
                     const double dx = c.x - sx[r], dy = c.y - sy[r], dz = c.z - sz[r];
                     double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    const bool drop = ((unsigned)(j - lo[r]) < (unsigned)len[r]) || (__double2hiint(r2) < 0x00100000);
+                    const bool drop = ((unsigned)(j - lo[r]) < (unsigned)len[r]) || (__double2hiint(r2) < kZeroR2Hi);
                     const double q = drop ? 0.0 : c.w;
                     r2 = drop ? 1.0 : r2;
                     if (POT) {
@@ -311,7 +317,7 @@ __global__ void __launch_bounds__(kBlock) pair_static_kernel(const PairArgs a) {
                     pt[r] = fma(c.w, rsqrt_f64(r2), pt[r]);
                 }
             }
-            careful = __any_sync(0xffffffffu, hmin < 0x3DDB7CDF);
+            careful = __any_sync(0xffffffffu, hmin < kZeroR2Hi);
             if (careful) {
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) pt[r] = 0.0;
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(kBlock) pair_static_kernel(const PairArgs a) {
                 for (int r = 0; r < ROWS; ++r) {
                     double r2 = fma(mx[r], c.x, fma(my[r], c.y, fma(mz[r], c.z, x2 + r2i[r])));
                     // zero distance (|r| < 1e-5 nm once the cancellation noise is allowed for): dropped
-                    const bool drop = ((unsigned)(j - rel[r]) < (unsigned)len[r]) || (__double2hiint(r2) < 0x3DDB7CDF);
+                    const bool drop = ((unsigned)(j - rel[r]) < (unsigned)len[r]) || (__double2hiint(r2) < kZeroR2Hi);
                     const double q = drop ? 0.0 : c.w;
                     r2 = drop ? 1.0 : r2;
                     pt[r] = fma(q, rsqrt_f64(r2), pt[r]);
