@@ -1,4 +1,4 @@
-// K1/K3: all-pairs potential + field of point charges at the Drude-shell rows.
+// K1/K3 and friends: all-pairs potential + field of point charges at the Drude-shell rows.
 //
 // Replaces the inter-molecular part of Ucoul and the static subtraction
 // (U_pol/polarization.py:63-91, :50-61) and, through the field, the reverse-mode gradient
@@ -9,19 +9,24 @@
 //                                        + 1/2 sum_{j in Drude, not in mol(i)} qs_j/|s_j - s_i| ]
 //   dU/dd_i    = -K qs_i sum_j q_j (x_j - s_i)/|x_j - s_i|^3   (+ intra + spring, finalize kernel)
 // i.e. rows = Drude shells held in registers, columns = every point charge (cores, then
-// shells) streamed through shared memory in tiles of kTileCols.  The d-independent part
-//   E0 = -K sum_i qs_i sum_{j not in mol(i)} (qc_j + qs_j/2)/|r_j - r_i|
-// is the same kernel without the field (K3).
+// shells) streamed through shared memory in tiles of kTileCols.
 //
-// Layout: columns are double4/float4 (x, y, z, q), section A (cores) and section B (shells)
-// each padded to a tile multiple with zero-charge dummies, so a tile is never mixed and the
-// 1/2 weight of shell columns is applied per tile.  Sites of a molecule are contiguous, so
-// the same-molecule exclusion of a row is one index interval per section: only tiles that
-// overlap an interval of some row of the warp take the predicated path.
-// Grid: x = row blocks (kBlock threads * ROWS rows), y = column splits; every (row block,
-// split) writes its partial sums once - no atomics, deterministic.
+// Kernels in this file
+//   pair_fp64_kernel<ROWS, POT, GRAD, MINB, SPLITF>  fp64 potential and/or field (K1); SPLITF keeps the
+//                                                     fields of the two column sections apart (core forces)
+//   pair_static_kernel<ROWS>                          fp64 static potential at the Drude cores (K3),
+//                                                     expanded squared distance, 10 DP ops per interaction
+//   pair_mixed_kernel<ROWS>                           field only: fixed-point coordinates, fp32 pair math,
+//                                                     fp64 accumulation
 //
-// Zero-distance pairs contribute nothing (polarization.py:33-42).
+// Layout: columns are double4 (x, y, z, q), section A (cores) and section B (shells) each padded to
+// a tile multiple with zero-charge dummies, so a tile is never mixed and the 1/2 weight of shell
+// columns is applied per tile.  Sites of a molecule are contiguous, so the same-molecule exclusion
+// of a row is one index interval per section: only tiles that overlap an interval of some row of
+// the warp take the predicated loop; every other tile runs a speculative compare-free loop that
+// is redone if it met a zero distance (zero-distance pairs contribute nothing,
+// polarization.py:33-42).  Grid: x = row blocks (kBlock threads * ROWS rows), y = column splits;
+// every (row block, split) writes its partial sums once - no atomics, deterministic.
 #include <cstdlib>
 
 #include "common.cuh"
