@@ -92,7 +92,7 @@ int upol_device_count(void) {
     return n;
 }
 
-int upol_system_create(upol_system **out, int device, int64_t nsite, const double *r_core,
+static int upol_system_create_impl(upol_system **out, int device, int64_t nsite, const double *r_core,
                        const double *q_core, const double *q_shell, const double *k,
                        const int32_t *mol_id, int64_t npair, const int32_t *pair_a,
                        const int32_t *pair_b, const double *pair_u) {
@@ -389,7 +389,7 @@ int upol_system_kernel_time(upol_system *s, double *ms_total, int32_t *launches)
     return UPOL_OK;
 }
 
-int upol_uind_core_gradient_dev(upol_system *s, const double *d, double *dudr, void *stream) {
+static int upol_uind_core_gradient_dev_impl(upol_system *s, const double *d, double *dudr, void *stream) {
     if (!s || !d || !dudr) return UPOL_ERR_ARG;
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -398,7 +398,7 @@ int upol_uind_core_gradient_dev(upol_system *s, const double *d, double *dudr, v
     return sys_core_forces(s, s->dc, dudr, st);
 }
 
-int upol_coulomb_static_dev(upol_system *s, double *out2, void *stream) {
+static int upol_coulomb_static_dev_impl(upol_system *s, double *out2, void *stream) {
     if (!s || !out2) return UPOL_ERR_ARG;
     DeviceGuard guard(s->device);
     return sys_coulomb_static(s, out2, (cudaStream_t)stream);
@@ -420,7 +420,7 @@ void upol_min_options_default(upol_min_options *o) {
     o->reserved = 0;
 }
 
-int upol_minimize_dev(upol_system *s, double *d, const upol_min_options *opts, upol_min_result *res, void *stream) {
+static int upol_minimize_dev_impl(upol_system *s, double *d, const upol_min_options *opts, upol_min_result *res, void *stream) {
     if (!s || !d || !res) return UPOL_ERR_ARG;
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -453,6 +453,52 @@ int upol_minimize_host(upol_system *s, double *d, const upol_min_options *opts, 
     UPOL_CUDA(cudaStreamSynchronize(0));
     memcpy(d, s->pin, sizeof(double) * n3);
     return rc;
+}
+
+// C ABI: no C++ exception may cross the boundary
+int upol_system_create(upol_system **out, int device, int64_t nsite, const double *r_core, const double *q_core,
+                       const double *q_shell, const double *k, const int32_t *mol_id, int64_t npair,
+                       const int32_t *pair_a, const int32_t *pair_b, const double *pair_u) {
+    try {
+        return upol_system_create_impl(out, device, nsite, r_core, q_core, q_shell, k, mol_id, npair, pair_a, pair_b, pair_u);
+    } catch (const std::bad_alloc &) {
+        return UPOL_ERR_ALLOC;
+    } catch (...) {
+        return UPOL_ERR_ARG;
+    }
+}
+
+// C ABI: no C++ exception may cross the boundary
+int upol_minimize_dev(upol_system *s, double *d, const upol_min_options *opts, upol_min_result *res, void *stream) {
+    try {
+        return upol_minimize_dev_impl(s, d, opts, res, stream);
+    } catch (const std::bad_alloc &) {
+        return UPOL_ERR_ALLOC;
+    } catch (...) {
+        return UPOL_ERR_ARG;
+    }
+}
+
+// C ABI: no C++ exception may cross the boundary
+int upol_uind_core_gradient_dev(upol_system *s, const double *d, double *dudr, void *stream) {
+    try {
+        return upol_uind_core_gradient_dev_impl(s, d, dudr, stream);
+    } catch (const std::bad_alloc &) {
+        return UPOL_ERR_ALLOC;
+    } catch (...) {
+        return UPOL_ERR_ARG;
+    }
+}
+
+// C ABI: no C++ exception may cross the boundary
+int upol_coulomb_static_dev(upol_system *s, double *out2, void *stream) {
+    try {
+        return upol_coulomb_static_dev_impl(s, out2, stream);
+    } catch (const std::bad_alloc &) {
+        return UPOL_ERR_ALLOC;
+    } catch (...) {
+        return UPOL_ERR_ARG;
+    }
 }
 
 }  // extern "C"

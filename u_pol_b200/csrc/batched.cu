@@ -11,6 +11,7 @@
 // minimize.cu.  Everything of a system lives in the shared memory slice of its warp; no global
 // traffic besides reading r and writing d, the energy vector and the iteration count.
 #include <algorithm>
+#include <new>
 #include <vector>
 
 #include "common.cuh"
@@ -319,7 +320,7 @@ __global__ void batched_bfgs_kernel(BatchTopo t, const double *__restrict__ site
 
 using namespace upol;
 
-extern "C" int upol_batched_minimize_dev(int device, int64_t nbatch, int64_t nsite, const double *r_core_dev,
+static int batched_minimize_impl(int device, int64_t nbatch, int64_t nsite, const double *r_core_dev,
                                          double *d_dev, const double *q_core, const double *q_shell,
                                          const double *k, const int32_t *mol_id, int64_t npair,
                                          const int32_t *pair_a, const int32_t *pair_b, const double *pair_u,
@@ -406,4 +407,21 @@ extern "C" int upol_batched_minimize_dev(int device, int64_t nbatch, int64_t nsi
     if (prev >= 0 && prev != device) cudaSetDevice(prev);
     if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
     return UPOL_OK;
+}
+
+// C ABI: no C++ exception may cross the boundary
+extern "C" int upol_batched_minimize_dev(int device, int64_t nbatch, int64_t nsite, const double *r_core_dev,
+                                         double *d_dev, const double *q_core, const double *q_shell,
+                                         const double *k, const int32_t *mol_id, int64_t npair,
+                                         const int32_t *pair_a, const int32_t *pair_b, const double *pair_u,
+                                         double tol, int32_t maxiter, double *energy_dev,
+                                         int32_t *iterations_dev, void *stream) {
+    try {
+        return batched_minimize_impl(device, nbatch, nsite, r_core_dev, d_dev, q_core, q_shell, k, mol_id, npair, pair_a,
+                                     pair_b, pair_u, tol, maxiter, energy_dev, iterations_dev, stream);
+    } catch (const std::bad_alloc &) {
+        return UPOL_ERR_ALLOC;
+    } catch (...) {
+        return UPOL_ERR_ARG;
+    }
 }

@@ -156,7 +156,7 @@ extern "C" int upol_comm_unique_id(unsigned char *id_bytes) {
     return UPOL_OK;
 }
 
-extern "C" int upol_system_attach_comm(upol_system *s, const unsigned char *id_bytes, int rank, int nranks) {
+extern "C" int upol_system_attach_comm(upol_system *s, const unsigned char *id_bytes, int rank, int nranks) try {
     if (!s || !id_bytes || nranks < 1 || rank < 0 || rank >= nranks) return UPOL_ERR_ARG;
     if (!api().ok) return UPOL_ERR_NCCL;
     comm_destroy(s);
@@ -183,6 +183,8 @@ extern "C" int upol_system_attach_comm(upol_system *s, const unsigned char *id_b
     int64_t ml, mh;
     shard_bounds(s->nmol, nranks, rank, &ml, &mh);
     return upol_system_set_row_range(s, ml, mh);
+} catch (...) {
+    return UPOL_ERR_ALLOC;
 }
 
 // ---- peer-memory exchange (CUDA IPC over NVLink) -------------------------------------------------
@@ -210,7 +212,7 @@ extern "C" int upol_system_p2p_export(upol_system *s, unsigned char *blob) {
     return UPOL_OK;
 }
 
-extern "C" int upol_system_p2p_attach(upol_system *s, const unsigned char *all) {
+extern "C" int upol_system_p2p_attach(upol_system *s, const unsigned char *all) try {
     if (!s || !all || s->nranks < 2 || !s->xchg_pack) return UPOL_ERR_ARG;
     int prev = -1;
     cudaGetDevice(&prev);
@@ -240,6 +242,8 @@ extern "C" int upol_system_p2p_attach(upol_system *s, const unsigned char *all) 
     if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); p2p_destroy(s); return UPOL_ERR_CUDA; }
     s->p2p = true;
     return UPOL_OK;
+} catch (...) {
+    return UPOL_ERR_ALLOC;
 }
 
 extern "C" int upol_system_p2p_disable(upol_system *s) {
