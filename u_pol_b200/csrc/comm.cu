@@ -189,7 +189,7 @@ extern "C" int upol_system_attach_comm(upol_system *s, const unsigned char *id_b
 
 // ---- peer-memory exchange (CUDA IPC over NVLink) -------------------------------------------------
 extern "C" int upol_system_p2p_export(upol_system *s, unsigned char *blob) {
-    if (!s || !blob || s->nranks < 2) return UPOL_ERR_ARG;
+    if (!s || !blob || s->nranks < 2 || s->nranks > 32) return UPOL_ERR_ARG;   // one warp polls the peers' flags
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(s->device);
