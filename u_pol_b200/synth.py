@@ -18,10 +18,11 @@ inter-molecular site distance is >= ``min_dist``.  The lattice is filled in 8 co
 (2x2x2 parity classes) so each pass is one vectorised numpy step.
 
 Deviation from SURVEY 8d, which proposed min_dist 0.25 nm at 33.4 / 9.1 nm^-3: random
-insertion of rigid molecules cannot reach that in usable time (minutes for 4 k imidazoles), so
-the defaults are min_dist 0.20 nm (still above the ~0.16 nm polarisation-catastrophe radius)
-with water at 33.4 nm^-3 and the imidazole liquid at 7.0 nm^-3.  Pair counts, and therefore
-the throughput metric, do not depend on the density.
+insertion of rigid molecules cannot reach that (a 33.4 nm^-3 water box already has seeds that
+cannot be completed at 0.20 nm), so the defaults are water at 33.4 nm^-3 with min_dist 0.18 nm
+and the imidazole liquid at 7.0 nm^-3 with 0.20 nm - both above the ~0.13-0.16 nm radius inside
+which a shell next to a bare charge has no local minimum.  Pair counts, and therefore the
+throughput metric, do not depend on the density.
 """
 from __future__ import annotations
 
@@ -59,6 +60,11 @@ def place_molecules(geom, nmol, density, seed, jitter=0.02, min_dist=0.25, max_t
     geom = geom - geom.mean(0)
     na = geom.shape[0]
     a = (1.0 / density) ** (1.0 / 3.0)
+    # Only the 26 neighbouring cells are tested, so a centre may leave its lattice point by at
+    # most dmax per component: sites of molecules two cells apart then stay >= min_dist apart.
+    dmax = 0.5 * (2.0 * a - min_dist - 2.0 * np.linalg.norm(geom, axis=1).max())
+    if dmax <= 0.0:
+        raise RuntimeError(f"density {density} leaves no room for min_dist {min_dist}")
     nx = int(np.ceil(nmol ** (1.0 / 3.0) - 1e-9))
     cells = np.stack(np.meshgrid(np.arange(nx), np.arange(nx), np.arange(nx), indexing="ij"), -1).reshape(-1, 3)
     cells = cells[:nmol]
@@ -84,7 +90,8 @@ def place_molecules(geom, nmol, density, seed, jitter=0.02, min_dist=0.25, max_t
             m = int(np.clip(2048 // n, 1, 64))          # candidates per molecule this round
             # stubborn molecules get a wider positional jitter so they can back away
             jit = jitter * (1.0 + attempt / 50.0)
-            centre = (cells[ids[todo]] + 0.5)[:, None, :] * a + rng.normal(scale=jit, size=(n, m, 3))
+            centre = (cells[ids[todo]] + 0.5)[:, None, :] * a + \
+                np.clip(rng.normal(scale=jit, size=(n, m, 3)), -dmax, dmax)
             rot = _random_rotations(rng, n * m).reshape(n, m, 3, 3)
             trial = centre[:, :, None, :] + np.einsum("nmij,aj->nmai", rot, geom)   # (n, m, na, 3)
             d = trial[:, :, :, None, None, :] - nb_pos[todo][:, None, None, :, :, :]  # (n,m,na,26,na,3)
@@ -112,7 +119,7 @@ def _box(monomer, nmol, density, seed, jitter, min_dist):
                        alpha=tile(m["alpha"]), thole_u=tile(m["thole_u"]), site_names=list(m["site_names"]))
 
 
-def water_box(nmol=3000, seed=2, density=33.4, jitter=0.02, min_dist=0.20):
+def water_box(nmol=3000, seed=2, density=33.4, jitter=0.02, min_dist=0.18):
     """BASELINE config 2: SWM4-NDP-style water, N = 4 nmol sites, N_D = nmol Drudes."""
     return _box("water", nmol, density, seed, jitter, min_dist)
 
