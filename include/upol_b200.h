@@ -240,7 +240,8 @@ int upol_system_set_kernel_timing(upol_system *sys, int enable);
 int upol_system_kernel_time(upol_system *sys, double *ms_total, int32_t *launches);
 
 /* FMA-pipe peak microbenchmarks used as roofline denominators: returns the
- * measured FLOP/s of a register-resident FMA chain on the current device, fp64 or fp32. */
+ * measured FLOP/s of a register-resident FMA chain on the current device: use_fp64 = 1 fp64 (DFMA),
+ * 0 fp32 (FFMA), 2 packed fp32 pairs (FFMA2, fma.rn.f32x2). */
 int upol_measure_fma_peak(int device, int use_fp64, double *flops_per_s);
 
 #ifdef __cplusplus

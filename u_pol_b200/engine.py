@@ -262,9 +262,11 @@ def shard_bounds(nmol, nranks, rank):
 
 
 def measure_fma_peak(fp64=True, device=0):
+    """FLOP/s of a register-resident FMA chain: fp64=True DFMA, False FFMA, "f32x2" packed FFMA2."""
     _require_cuda()
     v = C.c_double()
-    L.check(L.lib().upol_measure_fma_peak(int(device), int(bool(fp64)), C.byref(v)))
+    mode = 2 if fp64 == "f32x2" else int(bool(fp64))
+    L.check(L.lib().upol_measure_fma_peak(int(device), mode, C.byref(v)))
     return v.value
 
 
