@@ -363,6 +363,10 @@ def run_cuda(args):
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "kernel_ms": k_ms_avg, "launches_timed": k_n,
                          "interactions_per_launch": inter_local, "flop_per_interaction": FLOP_PER_INTERACTION,
+                         # the kernel issues 18.3 FP64-pipe instructions per interaction (SASS count: DFMA, DADD, DMUL;
+                         # DESIGN section 5): share of the DFMA-chain issue rate those instructions take up
+                         "fp64_instr_per_interaction": 18.3,
+                         "fp64_issue_frac": 18.3 * inter_local / (k_ms_avg * 1e-3) / (peak64 / 2.0),
                          "traffic": traffic,
                          "mixed_field_kernel": {"achieved": mixed_tflops, "peak": peak32 / 1e12,
                                                 "frac": mixed_tflops / (peak32 / 1e12), "unit": "TFLOP/s"}},
