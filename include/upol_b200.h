@@ -239,6 +239,19 @@ int upol_batched_minimize_dev(int device, int64_t nbatch, int64_t nsite,
 int upol_system_set_kernel_timing(upol_system *sys, int enable);
 int upol_system_kernel_time(upol_system *sys, double *ms_total, int32_t *launches);
 
+/* Periodic boundaries - an EXTENSION, not a replacement of reference code: shehan807/U_pol is gas
+ * phase only (benchmarks/OpenMM/water/calc_energy.py:80); SURVEY 8f lists this as "next".  With a box
+ * set, U_ind and its gradient (and therefore upol_minimize_*) are those of the orthorhombic periodic
+ * system, by direct Ewald summation with tin-foil boundary conditions and the reference's
+ * intra-molecular exclusions (definition and checker: oracle/ewald_dense.py).  box = 3 edge lengths in
+ * nm (NULL: back to open boundaries); kappa <= 0 picks 13 / min(box) (the real-space sum visits the
+ * nearest image only, so kappa * min(box) >= 12 is required); nmax = 0 keeps every reciprocal vector
+ * with exp(-k^2/4 kappa^2) >= exp(-41.5), nmax > 0 the cube |n| <= nmax.  Molecules must be whole
+ * (not wrapped atom by atom) and smaller than half the box.  fp64, one GPU; the core gradient, the
+ * separate static values and the mixed field are open-boundary only (UPOL_ERR_ARG). */
+int upol_system_set_periodic(upol_system *sys, const double *box, double kappa, int32_t nmax);
+int upol_system_periodic_info(upol_system *sys, double *box3, double *kappa, int32_t *n_kvectors);
+
 /* FMA-pipe peak microbenchmarks used as roofline denominators: returns the
  * measured FLOP/s of a register-resident FMA chain on the current device: use_fp64 = 1 fp64 (DFMA),
  * 0 fp32 (FFMA), 2 packed fp32 pairs (FFMA2, fma.rn.f32x2). */

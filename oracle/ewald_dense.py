@@ -80,7 +80,9 @@ def ewald_energy(X, Q, mol, box, kappa, nmax=None, images=1, kchunk=4096):
         for ny in cells:
             for nz in cells:
                 shift = torch.tensor([nx, ny, nz], dtype=_F64) * boxt
-                rr = torch.sqrt(((dx + shift) ** 2).sum(-1) + (torch.eye(M, dtype=_F64) if (nx, ny, nz) == (0, 0, 0) else 0.0))
+                # home cell: excluded pairs are masked below; keep their distance away from 0 so that a shell
+                # sitting exactly on its core (d = 0) does not put inf * 0 into the backward pass
+                rr = torch.sqrt(((dx + shift) ** 2).sum(-1) + (same.to(_F64) if (nx, ny, nz) == (0, 0, 0) else 0.0))
                 term = qq * torch.erfc(kappa * rr) / rr
                 if (nx, ny, nz) == (0, 0, 0):
                     term = torch.where(same, torch.zeros_like(term), term)

@@ -67,6 +67,8 @@ _SIGNATURES = {
     "upol_system_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "upol_system_kernel_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "upol_measure_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "upol_system_set_periodic": (C.c_int, [_P, _P, C.c_double, C.c_int32]),
+    "upol_system_periodic_info": (C.c_int, [_P, _P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -37,6 +37,7 @@ int dev_alloc(T **p, size_t n) {
 void free_system(upol_system *s) {
     if (!s) return;
     minimize_free(s);
+    ewald_free(s);
     comm_destroy(s);
     void *ptrs[] = {s->r, s->qc, s->qs, s->k, s->row_site, s->row_qs, s->row_k, s->exA_lo, s->exA_len,
                     s->exB_lo, s->exB_len, s->rowx, s->rowy, s->rowz, s->srowx, s->srowy, s->srowz,
@@ -204,6 +205,7 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
     TRY(dev_alloc(&s->cols_static, s->na_pad));
     TRY(dev_alloc(&s->th_ptr, s->nd + 1)); TRY(dev_alloc(&s->th_row, th_row.size())); TRY(dev_alloc(&s->th_u, th_u.size()));
     TRY(dev_alloc(&s->part, part_elems));
+    s->part_elems = part_elems;
     TRY(dev_alloc(&s->dc, 3 * s->nd)); TRY(dev_alloc(&s->gc, 3 * s->nd));
     s->n_eblock = (int)((std::max<int64_t>(s->nd, nsite) + 31) / 32) + 1;   // finalize blocks hold 32 rows
     TRY(dev_alloc(&s->eblock, 4 * (size_t)s->n_eblock));
@@ -316,6 +318,14 @@ int upol_system_set_row_range(upol_system *s, int64_t mol_lo, int64_t mol_hi) {
     return UPOL_OK;
 }
 
+int upol_system_periodic_info(upol_system *s, double *box, double *kappa, int32_t *nk) {
+    if (!s) return UPOL_ERR_ARG;
+    int n = 0;
+    int rc = ewald_info(s, box, kappa, &n);
+    if (rc == UPOL_OK && nk) *nk = n;
+    return rc;
+}
+
 int upol_uind_energy_grad_dev(upol_system *s, const double *d, int precision, double *energy,
                               double *grad, void *stream) {
     if (!s || !d || (!energy && !grad)) return UPOL_ERR_ARG;
@@ -389,8 +399,15 @@ int upol_system_kernel_time(upol_system *s, double *ms_total, int32_t *launches)
     return UPOL_OK;
 }
 
+static int upol_system_set_periodic_impl(upol_system *s, const double *box, double kappa, int nmax) {
+    if (!s) return UPOL_ERR_ARG;
+    DeviceGuard guard(s->device);
+    cudaDeviceSynchronize();                       // no evaluation may still be reading the old state
+    return ewald_setup(s, box, kappa, nmax);
+}
+
 static int upol_uind_core_gradient_dev_impl(upol_system *s, const double *d, double *dudr, void *stream) {
-    if (!s || !d || !dudr) return UPOL_ERR_ARG;
+    if (!s || !d || !dudr || s->ewald) return UPOL_ERR_ARG;     // open boundaries only
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = sys_gather_d(s, d, s->dc, st);
@@ -399,7 +416,7 @@ static int upol_uind_core_gradient_dev_impl(upol_system *s, const double *d, dou
 }
 
 static int upol_coulomb_static_dev_impl(upol_system *s, double *out2, void *stream) {
-    if (!s || !out2) return UPOL_ERR_ARG;
+    if (!s || !out2 || s->ewald) return UPOL_ERR_ARG;           // open boundaries only
     DeviceGuard guard(s->device);
     return sys_coulomb_static(s, out2, (cudaStream_t)stream);
 }
@@ -426,6 +443,7 @@ static int upol_minimize_dev_impl(upol_system *s, double *d, const upol_min_opti
     cudaStream_t st = (cudaStream_t)stream;
     upol_min_options o;
     if (opts) o = *opts; else upol_min_options_default(&o);
+    if (s->ewald && o.precision != UPOL_FP64) return UPOL_ERR_ARG;   // periodic boxes: fp64 only
     int rc = sys_gather_d(s, d, s->dc, st);
     if (rc) return rc;
     rc = minimize_compact(s, s->dc, &o, res, st);
@@ -494,6 +512,16 @@ int upol_uind_core_gradient_dev(upol_system *s, const double *d, double *dudr, v
 int upol_coulomb_static_dev(upol_system *s, double *out2, void *stream) {
     try {
         return upol_coulomb_static_dev_impl(s, out2, stream);
+    } catch (const std::bad_alloc &) {
+        return UPOL_ERR_ALLOC;
+    } catch (...) {
+        return UPOL_ERR_ARG;
+    }
+}
+
+int upol_system_set_periodic(upol_system *s, const double *box, double kappa, int32_t nmax) {
+    try {
+        return upol_system_set_periodic_impl(s, box, kappa, nmax);
     } catch (const std::bad_alloc &) {
         return UPOL_ERR_ALLOC;
     } catch (...) {

@@ -116,6 +116,7 @@ struct upol_system {
     double *th_u = nullptr;
     // work buffers
     double *part = nullptr;       // [max_split][kPartComps][nd_pad]
+    size_t part_elems = 0;        // doubles allocated for part
     double *dc = nullptr;         // [nd*3] compact displacements
     double *gc = nullptr;         // [nd*3] compact gradient
     double *eblock = nullptr;     // per-block energy partials
@@ -158,6 +159,9 @@ struct upol_system {
     // minimiser workspace (allocated on first use)
     void *min_ws = nullptr;
 
+    // periodic boundaries: Ewald state (ewald.cu), null = open boundaries
+    void *ewald = nullptr;
+
     // optional timing of the main pair kernel (bench.py roofline)
     bool timing = false;
     std::vector<cudaEvent_t> tev;   // start/stop pairs
@@ -199,6 +203,14 @@ int comm_allgather_rows(upol_system *s, double *vec3, cudaStream_t st);  // [nd*
 int comm_allgather_sites(upol_system *s, double *vec3, cudaStream_t st); // [nsite*3] in place by shard
 void comm_destroy(upol_system *s);
 void p2p_destroy(upol_system *s);
+
+// periodic boundaries (ewald.cu)
+int ewald_setup(upol_system *s, const double *box, double kappa, int nmax);
+int ewald_info(const upol_system *s, double *box, double *kappa, int *nk);
+void ewald_free(upol_system *s);
+void ewald_invalidate(upol_system *s);
+int ewald_static_part(upol_system *s, PairArgs a, int *n_slots, cudaStream_t st);
+int ewald_dynamic_part(upol_system *s, PairArgs a, int *n_slots, cudaStream_t st);
 
 // minimiser (minimize.cu)
 int minimize_compact(upol_system *s, double *d_compact, const upol_min_options *o,

@@ -331,7 +331,8 @@ int sys_static_part(upol_system *s, cudaStream_t st) {
     a.n_tiles = a.n_tiles_a;
     a.n_split = choose_split(s, a.n_rows, a.n_tiles, fp64_rows_per_block());
     if (a.n_rows > 0) {
-        int rc = launch_pair_static(a, st);
+        // periodic box: same rows and columns, Ewald pair function (ewald.cu) instead of 1/r
+        int rc = s->ewald ? ewald_static_part(s, a, &a.n_split, st) : launch_pair_static(a, st);
         if (rc) return rc;
         const int nb = (int)nblk(a.n_rows, kFinRows);
         finalize_static_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, a.n_split, s->part, a.part_stride,
@@ -348,6 +349,7 @@ int sys_static_part(upol_system *s, cudaStream_t st) {
 int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, double *energy_dev,
                      double *gcmp, cudaStream_t st) {
     if (o.precision != UPOL_FP64 && o.precision != UPOL_MIXED) return UPOL_ERR_ARG;
+    if (s->ewald && (o.precision != UPOL_FP64 || o.phase_switch || s->nranks > 1)) return UPOL_ERR_ARG;
     if (o.want_energy && !s->static_valid) {
         int rc = sys_static_part(s, st);
         if (rc) return rc;
@@ -376,7 +378,16 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
         const bool f64_field = o.want_grad && (!mixed_field_only || o.phase_switch);
         const bool mx_field = o.want_grad && mixed_field_only;
         int rc = UPOL_OK;
-        if (f64_field || o.want_energy) {
+        if (s->ewald) {
+            // periodic box: potential and field partials from the Ewald kernels, same slots
+            int slots = 0;
+            PairArgs b = a;
+            b.cols = s->cols;
+            rc = ewald_dynamic_part(s, b, &slots, st);
+            if (rc) return rc;
+            if (o.want_energy) split_pot = slots;
+            split_f64 = slots;
+        } else if (f64_field || o.want_energy) {
             // fp64 kernel: potential and/or field.  With a mixed field the fp64 launch carries the
             // potential only (energies are always fp64), unless the minimiser switches phases.
             PairArgs b = a;
@@ -391,7 +402,7 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
             if (o.want_energy) split_pot = split64;
             if (f64_field) split_f64 = split64;
         }
-        if (mx_field) {
+        if (mx_field && !s->ewald) {
             PairArgs b = a;
             b.cols = s->cols_f;                       // one section: core and shell of a site adjacent
             b.n_tiles = b.n_tiles_a = (int)(s->nm_pad / kTileCols);
@@ -527,6 +538,7 @@ int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream
                                                                     s->srowx, s->srowy, s->srowz);
     UPOL_CUDA(cudaGetLastError());
     s->static_valid = false;
+    ewald_invalidate(s);
     return UPOL_OK;
 }
 

@@ -251,6 +251,28 @@ class UindSystem:
         dist.barrier(group)
         return self.p2p
 
+    def set_periodic(self, box, kappa=None, nmax=0):
+        """Periodic boundaries (an extension: the reference is gas phase only).  ``box`` = 3 edge lengths
+        in nm of an orthorhombic cell, or None to return to open boundaries.  U_ind, its gradient and the
+        minimiser then refer to the periodic system (direct Ewald sum, tin-foil; definition and checker:
+        ``oracle/ewald_dense.py``).  ``kappa`` defaults to 13 / min(box); ``nmax`` > 0 replaces the default
+        reciprocal cut-off exp(-k^2/4kappa^2) >= exp(-41.5) by the cube |n| <= nmax.  fp64, one GPU."""
+        if box is None:
+            L.check(L.lib().upol_system_set_periodic(self._h, None, 0.0, 0), "upol_system_set_periodic")
+            return None
+        b = np.ascontiguousarray(np.asarray(box, dtype=np.float64).reshape(3))
+        L.check(L.lib().upol_system_set_periodic(self._h, b.ctypes.data, float(kappa or 0.0), int(nmax)),
+                "upol_system_set_periodic")
+        return self.periodic_info()
+
+    def periodic_info(self):
+        """{'box', 'kappa', 'n_kvectors'} of the periodic set-up, or None for open boundaries."""
+        b = np.zeros(3)
+        kap, nk = C.c_double(), C.c_int32()
+        if L.lib().upol_system_periodic_info(self._h, b.ctypes.data, C.byref(kap), C.byref(nk)) != 0:
+            return None
+        return {"box": b, "kappa": kap.value, "n_kvectors": nk.value}
+
     def set_row_range(self, mol_lo, mol_hi):
         L.check(L.lib().upol_system_set_row_range(self._h, int(mol_lo), int(mol_hi)))
         self._mrange = (int(mol_lo), int(mol_hi))
