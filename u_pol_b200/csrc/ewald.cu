@@ -48,7 +48,13 @@ namespace {
 
 constexpr double kZeroR2 = 1e-10;     // (1e-5 nm)^2: coincident pair, term dropped (polarization.py:33-42)
 
-__device__ __forceinline__ double wrap(double dx, double L, double iL) { return fma(-L, rint(dx * iL), dx); }
+// nearest image: dx - L * round(dx / L); the round-to-nearest-integer is the add/subtract of 1.5 * 2^52
+// (two full-rate DADDs, exact for |dx / L| < 2^51) instead of FRND.F64, which is a conversion-pipe op
+__device__ __forceinline__ double wrap(double dx, double L, double iL) {
+    const double t = dx * iL;
+    const double n = (t + 6755399441055744.0) - 6755399441055744.0;
+    return fma(-L, n, dx);
+}
 
 // g = erf(kappa r)/r and c with grad g(|x|) = c * x; series below kappa r = 0.05 (also r = 0).
 __device__ __forceinline__ void erf_over_r(double r2, double kappa, double c2, double &g, double &c) {
@@ -154,6 +160,13 @@ __global__ void ewald_cols0_kernel(int nd, int nb_pad, const double *__restrict_
     cols0[i] = i < nd ? make_double4(x[i], y[i], z[i], row_qs[i]) : make_double4(0.0, 0.0, 0.0, 0.0);
 }
 
+__device__ __forceinline__ void kahan_add(double &sum, double &comp, double term) {
+    const double y = term - comp;
+    const double t = sum + y;
+    comp = (t - sum) - y;
+    sum = t;
+}
+
 // Reciprocal-space potential / field at the rows, k range split over gridDim.y; block row y = 0 also
 // removes the row's own molecule (excluded pairs), which the structure factors contain.
 template <bool STATIC>
@@ -172,7 +185,7 @@ ewald_rows_kernel(const PairArgs a, const EwaldArgs w, int nk_pad, const int4 *_
     const double sx = a.rx[i], sy = a.ry[i], sz = a.rz[i];
     double f0 = sx * w.iLx, f1 = sy * w.iLy, f2 = sz * w.iLz;
     f0 -= rint(f0); f1 -= rint(f1); f2 -= rint(f2);
-    double pa = 0.0, pb = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+    double pa = 0.0, pb = 0.0, ca = 0.0, cb = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
     const int ntile = nk_pad / 128;
     const int k0 = (int)(((int64_t)ntile * blockIdx.y) / gridDim.y), k1 = (int)(((int64_t)ntile * (blockIdx.y + 1)) / gridDim.y);
     for (int t = k0; t < k1; ++t) {
@@ -187,8 +200,11 @@ ewald_rows_kernel(const PairArgs a, const EwaldArgs w, int nk_pad, const int4 *_
             const double2 c = s_c[j], sh = s_s[j];
             double si, co;
             sincospi(2.0 * fma((double)n.x, f0, fma((double)n.y, f1, (double)n.z * f2)), &si, &co);
-            pa = fma(A, fma(c.x, co, c.y * si), pa);
-            pb = fma(A, fma(sh.x, co, sh.y * si), pb);
+            // Kahan sums: each potential carries a self-like part of ~2 kappa/sqrt(pi) per unit charge that
+            // the static pass / the excluded-pair terms cancel again, so over 10^4-10^6 reciprocal vectors a
+            // plain running sum would leave sqrt(N_k) * eps of that part in U_ind
+            kahan_add(pa, ca, A * fma(c.x, co, c.y * si));
+            kahan_add(pb, cb, A * fma(sh.x, co, sh.y * si));
             if (!STATIC) {
                 const double gq = A * fma(c.y + sh.y, co, -(c.x + sh.x) * si);
                 gx = fma(gq, (double)n.x, gx); gy = fma(gq, (double)n.y, gy); gz = fma(gq, (double)n.z, gz);
