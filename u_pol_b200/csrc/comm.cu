@@ -158,7 +158,6 @@ extern "C" int upol_comm_unique_id(unsigned char *id_bytes) {
 
 extern "C" int upol_system_attach_comm(upol_system *s, const unsigned char *id_bytes, int rank, int nranks) try {
     if (!s || !id_bytes || nranks < 1 || rank < 0 || rank >= nranks) return UPOL_ERR_ARG;
-    if (s->ewald && nranks > 1) return UPOL_ERR_ARG;      // periodic boxes: one GPU
     if (!api().ok) return UPOL_ERR_NCCL;
     comm_destroy(s);
     int prev = -1;

@@ -16,7 +16,8 @@
 //
 // The partial sums go into the same part[split][comp][row] slots that finalize_rows_kernel /
 // finalize_static_kernel fold, so springs, Thole pairs, K*qs and the energy assembly are shared.
-// First correct version: fp64 only, one GPU, O(N^2) real space + O(N N_k) reciprocal space (no PME).
+// First correct version: fp64 only, O(N^2) real space + O(N N_k) reciprocal space (no PME); rows shard
+// over ranks like the open path (every rank forms the structure factors of all charges itself).
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -300,7 +301,7 @@ int ewald_setup(upol_system *s, const double *box, double kappa, int nmax) {
     ewald_free(s);
     s->static_valid = false;
     if (!box) return UPOL_OK;                       // back to open boundaries
-    if (!(box[0] > 0.0 && box[1] > 0.0 && box[2] > 0.0) || s->nranks > 1 || nmax < 0) return UPOL_ERR_ARG;
+    if (!(box[0] > 0.0 && box[1] > 0.0 && box[2] > 0.0) || nmax < 0) return UPOL_ERR_ARG;
     const double lmin = std::min(box[0], std::min(box[1], box[2]));
     if (!(kappa > 0.0)) kappa = 13.0 / lmin;        // erfc(kappa L/2) = erfc(6.5): nearest image suffices
     if (kappa * lmin < 12.0) return UPOL_ERR_ARG;   // the real-space sum only visits the nearest image

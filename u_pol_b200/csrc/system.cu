@@ -349,7 +349,7 @@ int sys_static_part(upol_system *s, cudaStream_t st) {
 int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, double *energy_dev,
                      double *gcmp, cudaStream_t st) {
     if (o.precision != UPOL_FP64 && o.precision != UPOL_MIXED) return UPOL_ERR_ARG;
-    if (s->ewald && (o.precision != UPOL_FP64 || o.phase_switch || s->nranks > 1)) return UPOL_ERR_ARG;
+    if (s->ewald && (o.precision != UPOL_FP64 || o.phase_switch)) return UPOL_ERR_ARG;
     if (o.want_energy && !s->static_valid) {
         int rc = sys_static_part(s, st);
         if (rc) return rc;
