@@ -47,6 +47,7 @@ struct EwaldArgs {
 
 namespace {
 
+constexpr int kRun = 16;              // reciprocal vectors per run of consecutive n_z (rows kernel)
 constexpr double kZeroR2 = 1e-10;     // (1e-5 nm)^2: coincident pair, term dropped (polarization.py:33-42)
 
 // nearest image: dx - L * round(dx / L); the round-to-nearest-integer is the add/subtract of 1.5 * 2^52
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(128)
 ewald_rows_kernel(const PairArgs a, const EwaldArgs w, int nk_pad, const int4 *__restrict__ kn,
                   const double *__restrict__ kA, const double2 *__restrict__ Sc, const double2 *__restrict__ Ss,
                   const double4 *__restrict__ cols, const double4 *__restrict__ cols_static, int na_pad, int slot0) {
-    __shared__ int4 s_n[128];
+    __shared__ double4 s_h[128 / kRun];          // per run: nx, ny, first nz
     __shared__ double s_A[128];
     __shared__ double2 s_c[128], s_s[128];
     if (a.gate != nullptr && (*a.gate & kGateDone) != 0) return;
@@ -186,30 +187,46 @@ ewald_rows_kernel(const PairArgs a, const EwaldArgs w, int nk_pad, const int4 *_
     const double sx = a.rx[i], sy = a.ry[i], sz = a.rz[i];
     double f0 = sx * w.iLx, f1 = sy * w.iLy, f2 = sz * w.iLz;
     f0 -= rint(f0); f1 -= rint(f1); f2 -= rint(f2);
+    double wr, wi;                                // one step along z: exp(2 pi i f_z)
+    sincospi(2.0 * f2, &wi, &wr);
     double pa = 0.0, pb = 0.0, ca = 0.0, cb = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
     const int ntile = nk_pad / 128;
     const int k0 = (int)(((int64_t)ntile * blockIdx.y) / gridDim.y), k1 = (int)(((int64_t)ntile * (blockIdx.y + 1)) / gridDim.y);
     for (int t = k0; t < k1; ++t) {
         __syncthreads();
-        s_n[tid] = kn[t * 128 + tid]; s_A[tid] = kA[t * 128 + tid];
+        s_A[tid] = kA[t * 128 + tid];
         s_c[tid] = Sc[t * 128 + tid]; s_s[tid] = Ss[t * 128 + tid];
+        if (tid < 128 / kRun) {
+            const int4 n = kn[t * 128 + tid * kRun];
+            s_h[tid] = make_double4((double)n.x, (double)n.y, (double)n.z, 0.0);
+        }
         __syncthreads();
-#pragma unroll 2
-        for (int j = 0; j < 128; ++j) {
-            const int4 n = s_n[j];
-            const double A = s_A[j];
-            const double2 c = s_c[j], sh = s_s[j];
+        for (int g = 0; g < 128 / kRun; ++g) {
+            // a run of kRun consecutive n_z at fixed (n_x, n_y): one sincospi, then the phase advances by
+            // complex multiplication (kRun steps of 1 ulp each; re-seeded at the next run)
+            const double4 h = s_h[g];
             double si, co;
-            sincospi(2.0 * fma((double)n.x, f0, fma((double)n.y, f1, (double)n.z * f2)), &si, &co);
-            // Kahan sums: each potential carries a self-like part of ~2 kappa/sqrt(pi) per unit charge that
-            // the static pass / the excluded-pair terms cancel again, so over 10^4-10^6 reciprocal vectors a
-            // plain running sum would leave sqrt(N_k) * eps of that part in U_ind
-            kahan_add(pa, ca, A * fma(c.x, co, c.y * si));
-            kahan_add(pb, cb, A * fma(sh.x, co, sh.y * si));
-            if (!STATIC) {
-                const double gq = A * fma(c.y + sh.y, co, -(c.x + sh.x) * si);
-                gx = fma(gq, (double)n.x, gx); gy = fma(gq, (double)n.y, gy); gz = fma(gq, (double)n.z, gz);
+            sincospi(2.0 * fma(h.x, f0, fma(h.y, f1, h.z * f2)), &si, &co);
+            double lg = 0.0, lgz = 0.0, nz = h.z;
+#pragma unroll
+            for (int u = 0; u < kRun; ++u) {
+                const int j = g * kRun + u;
+                const double A = s_A[j];
+                const double2 c = s_c[j], sh = s_s[j];
+                // Kahan sums: each potential carries a self-like part of ~2 kappa/sqrt(pi) per unit charge
+                // that the static pass / the excluded-pair terms cancel again, so over 10^4-10^6 reciprocal
+                // vectors a plain running sum would leave sqrt(N_k) * eps of that part in U_ind
+                kahan_add(pa, ca, A * fma(c.x, co, c.y * si));
+                kahan_add(pb, cb, A * fma(sh.x, co, sh.y * si));
+                if (!STATIC) {
+                    const double gq = A * fma(c.y + sh.y, co, -(c.x + sh.x) * si);
+                    lg += gq; lgz = fma(gq, nz, lgz); nz += 1.0;
+                }
+                const double t2 = fma(co, wr, -si * wi);
+                si = fma(co, wi, si * wr);
+                co = t2;
             }
+            if (!STATIC) { gx = fma(h.x, lg, gx); gy = fma(h.y, lg, gy); gz += lgz; }
         }
     }
     const double two_pi = 2.0 * kPi;
@@ -314,19 +331,34 @@ int ewald_setup(upol_system *s, const double *box, double kappa, int nmax) {
     int lim[3];
     for (int c = 0; c < 3; ++c) lim[c] = nmax > 0 ? nmax : (int)std::floor(kmax * box[c] / (2.0 * kPi));
     const double vol = box[0] * box[1] * box[2];
+    // Lines of consecutive n_z at fixed (n_x, n_y), each padded to a multiple of kRun with zero-weight
+    // entries that continue the line, so that the rows kernel can advance the phase by recurrence.
     std::vector<int4> kn;
     std::vector<double> kA;
+    int n_true = 0;
     for (int nx = 0; nx <= lim[0]; ++nx)
-        for (int ny = (nx == 0 ? 0 : -lim[1]); ny <= lim[1]; ++ny)
+        for (int ny = (nx == 0 ? 0 : -lim[1]); ny <= lim[1]; ++ny) {
+            int z_lo = 0, z_hi = -1;
+            bool any = false;
             for (int nz = ((nx == 0 && ny == 0) ? 1 : -lim[2]); nz <= lim[2]; ++nz) {
                 const double kx = 2.0 * kPi * nx / box[0], ky = 2.0 * kPi * ny / box[1], kz = 2.0 * kPi * nz / box[2];
-                const double k2 = kx * kx + ky * ky + kz * kz;
-                if (nmax == 0 && k2 > kmax * kmax) continue;
-                kn.push_back(make_int4(nx, ny, nz, 0));
-                kA.push_back(8.0 * kPi / vol * std::exp(-k2 / (4.0 * kappa * kappa)) / k2);
+                if (nmax == 0 && kx * kx + ky * ky + kz * kz > kmax * kmax) continue;
+                if (!any) { z_lo = nz; any = true; }
+                z_hi = nz;
             }
-    e->nk = (int)kn.size();
-    e->nk_pad = (int)round_up(std::max<int64_t>(e->nk, 1), 128);
+            if (!any) continue;
+            const int len = z_hi - z_lo + 1, padded = (int)round_up(len, kRun);
+            for (int u = 0; u < padded; ++u) {
+                const int nz = z_lo + u;
+                const double kx = 2.0 * kPi * nx / box[0], ky = 2.0 * kPi * ny / box[1], kz = 2.0 * kPi * nz / box[2];
+                const double k2 = kx * kx + ky * ky + kz * kz;
+                kn.push_back(make_int4(nx, ny, nz, 0));
+                kA.push_back(u < len ? 8.0 * kPi / vol * std::exp(-k2 / (4.0 * kappa * kappa)) / k2 : 0.0);
+            }
+            n_true += len;
+        }
+    e->nk = n_true;
+    e->nk_pad = (int)round_up(std::max<int64_t>((int64_t)kn.size(), 1), 128);
     kn.resize(e->nk_pad, make_int4(0, 0, 0, 0));
     kA.resize(e->nk_pad, 0.0);
     auto fail = [&](int rc) { ewald_free(s); return rc; };
