@@ -36,6 +36,8 @@ struct EwaldState {
     double2 *Ss0 = nullptr;    // [nk_pad] ... of the shells sitting on their cores (d = 0)
     double2 *Ssd = nullptr;    // [nk_pad] ... of the shells at r - d
     double4 *cols0 = nullptr;  // [nb_pad] shells at their cores: x, y, z, qs
+    double2 *rec = nullptr;    // [3 * max(na_pad, nb_pad)] per-charge records of the structure-factor pass
+    double2 *partial = nullptr;  // [kSfacChunks][nk_pad] per-chunk partial structure factors
     bool sfac_valid = false;   // Sc, Ss0, cols0 match the current core positions
 };
 
@@ -47,6 +49,7 @@ struct EwaldArgs {
 
 namespace {
 
+constexpr int kSfacChunks = 16;       // charge chunks of the structure-factor pass (partials per k)
 constexpr int kRun = 16;              // reciprocal vectors per run of consecutive n_z (rows kernel)
 constexpr double kZeroR2 = 1e-10;     // (1e-5 nm)^2: coincident pair, term dropped (polarization.py:33-42)
 
@@ -124,34 +127,87 @@ __global__ void __launch_bounds__(kBlock) ewald_real_kernel(const PairArgs a, co
     }
 }
 
-// S(k) = sum_j q_j exp(i k.x_j) for one charge set; one thread per reciprocal vector.
-__global__ void __launch_bounds__(128) ewald_sfac_kernel(int ncols, const double4 *__restrict__ cols,
-                                                         const int4 *__restrict__ kn, const EwaldArgs w,
-                                                         const int *__restrict__ gate, double2 *__restrict__ out) {
-    __shared__ double4 sh[128];
+// Structure factors S(k) = sum_j q_j exp(i k.x_j) of one charge set, in three launches:
+//   prep    per charge: fractional coordinates (reduced to [-1/2, 1/2]), q, and the z step exp(2 pi i f_z);
+//   partial threads own charges, blocks own (charge chunk, range of runs): per run of kRun consecutive
+//           n_z one sincospi per charge, then the phase advances by complex multiplication while
+//           2 * kRun register accumulators collect q * phase; the block folds them through shared
+//           memory in fixed order and writes one partial per (chunk, k);
+//   fold    S(k) = sum over chunks (fixed order: deterministic).
+__global__ void ewald_prep_kernel(int ncols, const double4 *__restrict__ cols, const EwaldArgs w, const int *__restrict__ gate,
+                                  double2 *__restrict__ rec) {
+    if (gate != nullptr && (*gate & kGateDone) != 0) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    const double4 c = cols[j];
+    double fx = c.x * w.iLx, fy = c.y * w.iLy, fz = c.z * w.iLz;
+    fx -= rint(fx); fy -= rint(fy); fz -= rint(fz);
+    double wr, wi;
+    sincospi(2.0 * fz, &wi, &wr);
+    rec[3 * (int64_t)j] = make_double2(fx, fy);
+    rec[3 * (int64_t)j + 1] = make_double2(fz, c.w);
+    rec[3 * (int64_t)j + 2] = make_double2(wr, wi);
+}
+
+constexpr int kSfacPad = 129;      // row stride of the fold buffer (bank-conflict free column reads)
+
+__global__ void __launch_bounds__(128)
+ewald_sfac_partial_kernel(int ncols, const double2 *__restrict__ rec, int nk_pad, const int4 *__restrict__ kn,
+                          const int *__restrict__ gate, double2 *__restrict__ partial) {
+    __shared__ double fold[2 * kRun][kSfacPad];
+    __shared__ double quart[4][2 * kRun];
     if (gate != nullptr && (*gate & kGateDone) != 0) return;
     const int tid = threadIdx.x;
-    const int4 n = kn[blockIdx.x * 128 + tid];
-    const double nx = n.x, ny = n.y, nz = n.z;
-    double re = 0.0, im = 0.0;
-    for (int base = 0; base < ncols; base += 128) {
+    const int per = (ncols + gridDim.x - 1) / gridDim.x;
+    const int c0 = blockIdx.x * per, c1 = min(ncols, c0 + per);
+    const int nrun = nk_pad / kRun;
+    const int r0 = (int)(((int64_t)nrun * blockIdx.y) / gridDim.y), r1 = (int)(((int64_t)nrun * (blockIdx.y + 1)) / gridDim.y);
+    for (int run = r0; run < r1; ++run) {
+        const int4 n = kn[run * kRun];
+        const double nx = n.x, ny = n.y, nz = n.z;
+        double are[kRun], aim[kRun];
+#pragma unroll
+        for (int u = 0; u < kRun; ++u) are[u] = aim[u] = 0.0;
+        for (int j = c0 + tid; j < c1; j += 128) {
+            const double2 a = rec[3 * (int64_t)j], b = rec[3 * (int64_t)j + 1], st = rec[3 * (int64_t)j + 2];
+            double si, co;
+            sincospi(2.0 * fma(nx, a.x, fma(ny, a.y, nz * b.x)), &si, &co);
+            co *= b.y; si *= b.y;                      // carry q inside the phase
+#pragma unroll
+            for (int u = 0; u < kRun; ++u) {
+                are[u] += co; aim[u] += si;
+                const double t2 = fma(co, st.x, -si * st.y);
+                si = fma(co, st.y, si * st.x);
+                co = t2;
+            }
+        }
         __syncthreads();
-        double4 c = cols[base + tid];
-        // fractional coordinates reduced to [-1/2, 1/2]: the phase stays small and exact in the integers
-        c.x = c.x * w.iLx; c.x -= rint(c.x);
-        c.y = c.y * w.iLy; c.y -= rint(c.y);
-        c.z = c.z * w.iLz; c.z -= rint(c.z);
-        sh[tid] = c;
+#pragma unroll
+        for (int u = 0; u < kRun; ++u) { fold[u][tid] = are[u]; fold[kRun + u][tid] = aim[u]; }
         __syncthreads();
-#pragma unroll 4
-        for (int j = 0; j < 128; ++j) {
-            const double4 p = sh[j];
-            double s, co;
-            sincospi(2.0 * fma(nx, p.x, fma(ny, p.y, nz * p.z)), &s, &co);
-            re = fma(p.w, co, re); im = fma(p.w, s, im);
+        {
+            const int v = tid & (2 * kRun - 1), q = tid / (2 * kRun);     // 128 threads = 32 values x 4 quarters
+            double sum = 0.0;
+            for (int t = 0; t < 32; ++t) sum += fold[v][q * 32 + t];
+            quart[q][v] = sum;
+        }
+        __syncthreads();
+        if (tid < kRun) {
+            const double re = (quart[0][tid] + quart[1][tid]) + (quart[2][tid] + quart[3][tid]);
+            const double im = (quart[0][kRun + tid] + quart[1][kRun + tid]) + (quart[2][kRun + tid] + quart[3][kRun + tid]);
+            partial[(int64_t)blockIdx.x * nk_pad + run * kRun + tid] = make_double2(re, im);
         }
     }
-    out[blockIdx.x * 128 + tid] = make_double2(re, im);
+}
+
+__global__ void ewald_sfac_fold_kernel(int nchunk, int nk_pad, const double2 *__restrict__ partial, const int *__restrict__ gate,
+                                       double2 *__restrict__ out) {
+    if (gate != nullptr && (*gate & kGateDone) != 0) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nk_pad) return;
+    double re = 0.0, im = 0.0;
+    for (int c = 0; c < nchunk; ++c) { const double2 p = partial[(int64_t)c * nk_pad + k]; re += p.x; im += p.y; }
+    out[k] = make_double2(re, im);
 }
 
 __global__ void ewald_cols0_kernel(int nd, int nb_pad, const double *__restrict__ x, const double *__restrict__ y,
@@ -304,7 +360,7 @@ void choose_slots(const upol_system *s, const EwaldState *e, int n_rows, int n_t
 void ewald_free(upol_system *s) {
     EwaldState *e = static_cast<EwaldState *>(s->ewald);
     if (!e) return;
-    void *ptrs[] = {e->kn, e->kA, e->Sc, e->Ss0, e->Ssd, e->cols0};
+    void *ptrs[] = {e->kn, e->kA, e->Sc, e->Ss0, e->Ssd, e->cols0, e->rec, e->partial};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete e;
     s->ewald = nullptr;
@@ -367,7 +423,9 @@ int ewald_setup(upol_system *s, const double *box, double kappa, int nmax) {
         cudaMalloc((void **)&e->Sc, sizeof(double2) * e->nk_pad) != cudaSuccess ||
         cudaMalloc((void **)&e->Ss0, sizeof(double2) * e->nk_pad) != cudaSuccess ||
         cudaMalloc((void **)&e->Ssd, sizeof(double2) * e->nk_pad) != cudaSuccess ||
-        cudaMalloc((void **)&e->cols0, sizeof(double4) * std::max<int64_t>(s->nb_pad, 1)) != cudaSuccess) {
+        cudaMalloc((void **)&e->cols0, sizeof(double4) * std::max<int64_t>(s->nb_pad, 1)) != cudaSuccess ||
+        cudaMalloc((void **)&e->rec, sizeof(double2) * 3 * std::max<int64_t>(std::max(s->na_pad, s->nb_pad), 1)) != cudaSuccess ||
+        cudaMalloc((void **)&e->partial, sizeof(double2) * (size_t)kSfacChunks * e->nk_pad) != cudaSuccess) {
         cudaGetLastError();
         return fail(UPOL_ERR_ALLOC);
     }
@@ -388,14 +446,33 @@ int ewald_info(const upol_system *s, double *box, double *kappa, int *nk) {
     return UPOL_OK;
 }
 
+static int launch_sfac(EwaldState *e, int ncols, const double4 *cols, const EwaldArgs &w, const int *gate,
+                       double2 *out, cudaStream_t st) {
+    if (ncols <= 0) {
+        UPOL_CUDA(cudaMemsetAsync(out, 0, sizeof(double2) * e->nk_pad, st));
+        return UPOL_OK;
+    }
+    ewald_prep_kernel<<<nblk(ncols, 256), 256, 0, st>>>(ncols, cols, w, gate, e->rec);
+    const int chunks = std::max(1, std::min(kSfacChunks, (ncols + 1023) / 1024));
+    const int nrun = e->nk_pad / kRun;
+    const int ry = std::max(1, std::min(nrun, (148 * 4 + chunks - 1) / chunks));
+    dim3 grid((unsigned)chunks, (unsigned)ry);
+    ewald_sfac_partial_kernel<<<grid, 128, 0, st>>>(ncols, e->rec, e->nk_pad, e->kn, gate, e->partial);
+    ewald_sfac_fold_kernel<<<nblk(e->nk_pad, 256), 256, 0, st>>>(chunks, e->nk_pad, e->partial, gate, out);
+    UPOL_CUDA(cudaGetLastError());
+    return UPOL_OK;
+}
+
 // structure factors that depend on the core positions only
 static int ewald_static_sfac(upol_system *s, EwaldState *e, const EwaldArgs &w, cudaStream_t st) {
     if (e->sfac_valid) return UPOL_OK;
     ewald_cols0_kernel<<<nblk(s->nb_pad, 256), 256, 0, st>>>((int)s->nd, (int)s->nb_pad, s->srowx, s->srowy, s->srowz,
                                                              s->row_qs, e->cols0);
-    ewald_sfac_kernel<<<e->nk_pad / 128, 128, 0, st>>>((int)s->na_pad, s->cols, e->kn, w, nullptr, e->Sc);
-    ewald_sfac_kernel<<<e->nk_pad / 128, 128, 0, st>>>((int)s->nb_pad, e->cols0, e->kn, w, nullptr, e->Ss0);
     UPOL_CUDA(cudaGetLastError());
+    int rc = launch_sfac(e, (int)s->na_pad, s->cols, w, nullptr, e->Sc, st);
+    if (rc) return rc;
+    rc = launch_sfac(e, (int)s->nb_pad, e->cols0, w, nullptr, e->Ss0, st);
+    if (rc) return rc;
     e->sfac_valid = true;
     return UPOL_OK;
 }
@@ -427,7 +504,8 @@ int ewald_dynamic_part(upol_system *s, PairArgs a, int *n_slots, cudaStream_t st
     const EwaldArgs w = make_args(e);
     int rc = ewald_static_sfac(s, e, w, st);
     if (rc) return rc;
-    ewald_sfac_kernel<<<e->nk_pad / 128, 128, 0, st>>>((int)s->nb_pad, s->cols + s->na_pad, e->kn, w, a.gate, e->Ssd);
+    rc = launch_sfac(e, (int)s->nb_pad, s->cols + s->na_pad, w, a.gate, e->Ssd, st);
+    if (rc) return rc;
     int s_real, s_rec;
     choose_slots(s, e, a.n_rows, a.n_tiles, a.part_stride, s_real, s_rec);
     a.n_split = s_real;
