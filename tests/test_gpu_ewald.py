@@ -119,3 +119,25 @@ def test_medium_box_against_the_oracle():
     a = (1.0 / 7.0) ** (1.0 / 3.0)
     box = np.array([4 * a + 0.1] * 3)                         # the liquid's own cell (+ margin for the faces)
     _compare(s, D, box)
+
+
+def test_broken_or_oversized_molecules_are_refused():
+    s = synth.imidazole_box(4, seed=13)
+    D = np.zeros_like(s.r_core)
+    box = _box_for(s, pad=0.8)
+    sys_ = UindSystem.from_drude_system(s)
+    sys_.set_periodic(box)
+    sys_.energy_grad(D)
+    r2 = s.r_core.copy()
+    r2[1, 3] += [box[0], 0.0, 0.0]                            # one atom wrapped on its own: molecule no longer whole
+    sys_.set_positions(r2)
+    with pytest.raises(UpolError):
+        sys_.energy_grad(D)
+    with pytest.raises(UpolError):
+        sys_.minimize()
+    sys_.set_positions(s.r_core)
+    sys_.energy_grad(D)                                       # recovers with a valid geometry
+    ext = np.ptp(s.r_core[0], axis=0).max()
+    sys_.set_periodic([1.5 * ext, 10.0, 10.0])                # molecule larger than half the cell
+    with pytest.raises(UpolError):
+        sys_.energy_grad(D)

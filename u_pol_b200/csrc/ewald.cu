@@ -39,6 +39,8 @@ struct EwaldState {
     double2 *rec = nullptr;    // [3 * max(na_pad, nb_pad)] per-charge records of the structure-factor pass
     double2 *partial = nullptr;  // [kSfacChunks][nk_pad] per-chunk partial structure factors
     bool sfac_valid = false;   // Sc, Ss0, cols0 match the current core positions
+    int *mol_site0 = nullptr, *mol_nsite = nullptr;   // [nmol] site interval of a molecule
+    int *bad = nullptr;        // [1] set by the geometry check
 };
 
 struct EwaldArgs {
@@ -223,6 +225,21 @@ __global__ void ewald_sfac_fold_kernel(int nchunk, int nk_pad, const double2 *__
     out[k] = make_double2(re, im);
 }
 
+// Molecules must be whole (not wrapped atom by atom) and smaller than half the box: the excluded-pair
+// terms use the direct intra-molecular distance and the real-space sum the nearest image only.
+__global__ void ewald_check_molecules_kernel(int nmol, const int *__restrict__ site0, const int *__restrict__ nsite,
+                                             const double *__restrict__ r, double hx, double hy, double hz,
+                                             int *__restrict__ bad) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmol) return;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = site0[m]; i < site0[m] + nsite[m]; ++i)
+        for (int c = 0; c < 3; ++c) { const double v = r[3 * i + c]; lo[c] = fmin(lo[c], v); hi[c] = fmax(hi[c], v); }
+    const bool ok = nsite[m] == 0 || (hi[0] - lo[0] < hx && hi[1] - lo[1] < hy && hi[2] - lo[2] < hz &&
+                                      isfinite(hi[0]) && isfinite(hi[1]) && isfinite(hi[2]));
+    if (!ok) atomicOr(bad, 1);
+}
+
 __global__ void ewald_cols0_kernel(int nd, int nb_pad, const double *__restrict__ x, const double *__restrict__ y,
                                    const double *__restrict__ z, const double *__restrict__ row_qs,
                                    double4 *__restrict__ cols0) {
@@ -373,7 +390,7 @@ void choose_slots(const upol_system *s, const EwaldState *e, int n_rows, int n_t
 void ewald_free(upol_system *s) {
     EwaldState *e = static_cast<EwaldState *>(s->ewald);
     if (!e) return;
-    void *ptrs[] = {e->kn, e->kA, e->Sc, e->Ss0, e->Ssd, e->cols0, e->rec, e->partial};
+    void *ptrs[] = {e->kn, e->kA, e->Sc, e->Ss0, e->Ssd, e->cols0, e->rec, e->partial, e->mol_site0, e->mol_nsite, e->bad};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete e;
     s->ewald = nullptr;
@@ -438,12 +455,17 @@ int ewald_setup(upol_system *s, const double *box, double kappa, int nmax) {
         cudaMalloc((void **)&e->Ssd, sizeof(double2) * e->nk_pad) != cudaSuccess ||
         cudaMalloc((void **)&e->cols0, sizeof(double4) * std::max<int64_t>(s->nb_pad, 1)) != cudaSuccess ||
         cudaMalloc((void **)&e->rec, sizeof(double2) * 3 * std::max<int64_t>(std::max(s->na_pad, s->nb_pad), 1)) != cudaSuccess ||
-        cudaMalloc((void **)&e->partial, sizeof(double2) * (size_t)kSfacChunks * e->nk_pad) != cudaSuccess) {
+        cudaMalloc((void **)&e->partial, sizeof(double2) * (size_t)kSfacChunks * e->nk_pad) != cudaSuccess ||
+        cudaMalloc((void **)&e->mol_site0, sizeof(int) * std::max<int64_t>(s->nmol, 1)) != cudaSuccess ||
+        cudaMalloc((void **)&e->mol_nsite, sizeof(int) * std::max<int64_t>(s->nmol, 1)) != cudaSuccess ||
+        cudaMalloc((void **)&e->bad, sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
         return fail(UPOL_ERR_ALLOC);
     }
     if (cudaMemcpy(e->kn, kn.data(), sizeof(int4) * e->nk_pad, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(e->kA, kA.data(), sizeof(double) * e->nk_pad, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaMemcpy(e->kA, kA.data(), sizeof(double) * e->nk_pad, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(e->mol_site0, s->h_mol_site0.data(), sizeof(int) * s->nmol, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(e->mol_nsite, s->h_mol_nsite.data(), sizeof(int) * s->nmol, cudaMemcpyHostToDevice) != cudaSuccess) {
         set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
         return fail(UPOL_ERR_CUDA);
     }
@@ -479,6 +501,14 @@ static int launch_sfac(EwaldState *e, int ncols, const double4 *cols, const Ewal
 // structure factors that depend on the core positions only
 static int ewald_static_sfac(upol_system *s, EwaldState *e, const EwaldArgs &w, cudaStream_t st) {
     if (e->sfac_valid) return UPOL_OK;
+    // once per geometry: refuse molecules that are broken across the cell or too large for it
+    UPOL_CUDA(cudaMemsetAsync(e->bad, 0, sizeof(int), st));
+    ewald_check_molecules_kernel<<<nblk(s->nmol, 128), 128, 0, st>>>((int)s->nmol, e->mol_site0, e->mol_nsite, s->r,
+                                                                     0.5 * e->box[0], 0.5 * e->box[1], 0.5 * e->box[2], e->bad);
+    int bad = 0;
+    UPOL_CUDA(cudaMemcpyAsync(&bad, e->bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    UPOL_CUDA(cudaStreamSynchronize(st));
+    if (bad) return UPOL_ERR_ARG;
     ewald_cols0_kernel<<<nblk(s->nb_pad, 256), 256, 0, st>>>((int)s->nd, (int)s->nb_pad, s->srowx, s->srowy, s->srowz,
                                                              s->row_qs, e->cols0);
     UPOL_CUDA(cudaGetLastError());
