@@ -416,6 +416,8 @@ int ewald_setup(upol_system *s, const double *box, double kappa, int nmax) {
     const double kmax = 2.0 * kappa * std::sqrt(41.5);
     int lim[3];
     for (int c = 0; c < 3; ++c) lim[c] = nmax > 0 ? nmax : (int)std::floor(kmax * box[c] / (2.0 * kPi));
+    // refuse set-ups whose reciprocal list would not fit comfortably (a cube needs ~5e4 vectors)
+    if ((double)(lim[0] + 1) * (2.0 * lim[1] + 1) * (2.0 * lim[2] + 1) > 3.2e7) { ewald_free(s); return UPOL_ERR_ARG; }
     const double vol = box[0] * box[1] * box[2];
     // Lines of consecutive n_z at fixed (n_x, n_y), each padded to a multiple of kRun with zero-weight
     // entries that continue the line, so that the rows kernel can advance the phase by recurrence.
