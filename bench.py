@@ -310,13 +310,15 @@ def run_cuda(args):
     peak32 = measure_fma_peak(False, local_rank)
     k_ms_avg = k_ms / max(k_n, 1)
     achieved = FLOP_PER_INTERACTION * inter_local / (k_ms_avg * 1e-3) / 1e12
-    traffic = None
+    traffic = pipe_ncu = None
     tfile = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tfile):
         try:
-            traffic = json.load(open(tfile)).get("pair_fp64_kernel_dram_bytes_per_launch")
+            tj = json.load(open(tfile))
+            traffic = tj.get("pair_fp64_kernel_dram_bytes_per_launch")
+            pipe_ncu = tj.get("pair_fp64_kernel_fp64_pipe_active_pct")      # from the committed ncu capture, not live
         except Exception:
-            traffic = None
+            traffic = pipe_ncu = None
     # mixed-precision field kernel, for context
     sysm.set_kernel_timing(True)
     for _ in range(3):
@@ -367,6 +369,7 @@ def run_cuda(args):
                          # DESIGN section 5): share of the DFMA-chain issue rate those instructions take up
                          "fp64_instr_per_interaction": 18.3,
                          "fp64_issue_frac": 18.3 * inter_local / (k_ms_avg * 1e-3) / (peak64 / 2.0),
+                         "fp64_pipe_active_pct_ncu": pipe_ncu,
                          "traffic": traffic,
                          "mixed_field_kernel": {"achieved": mixed_tflops, "peak": peak32 / 1e12,
                                                 "frac": mixed_tflops / (peak32 / 1e12), "unit": "TFLOP/s"}},
