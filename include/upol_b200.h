@@ -247,8 +247,9 @@ int upol_system_kernel_time(upol_system *sys, double *ms_total, int32_t *launche
  * nm (NULL: back to open boundaries); kappa <= 0 picks 13 / min(box) (the real-space sum visits the
  * nearest image only, so kappa * min(box) >= 12 is required); nmax = 0 keeps every reciprocal vector
  * with exp(-k^2/4 kappa^2) >= exp(-41.5), nmax > 0 the cube |n| <= nmax.  Molecules must be whole
- * (not wrapped atom by atom) and smaller than half the box.  fp64; row shards work as in the open case;
- * the core gradient, the separate static values and the mixed field are open-boundary only
+ * (not wrapped atom by atom) and smaller than half the box (checked on the device, UPOL_ERR_ARG
+ * otherwise).  fp64; row shards work as in the open case; upol_uind_core_gradient_dev gives the
+ * periodic dU_ind/dr_core; the separate static values and the mixed field are open-boundary only
  * (UPOL_ERR_ARG). */
 int upol_system_set_periodic(upol_system *sys, const double *box, double kappa, int32_t nmax);
 int upol_system_periodic_info(upol_system *sys, double *box3, double *kappa, int32_t *n_kvectors);

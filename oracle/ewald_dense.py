@@ -121,7 +121,7 @@ def _thole_intra(R, D, qis, qjs, u):
 def u_ind_pbc(r_core, D, q_core, q_shell, k, thole_u, box, kappa, nmax=None, images=1):
     """Periodic U_ind (torch scalar; differentiable in D).  Compact inputs: r_core, D (nmol,natoms,3);
     q_core, q_shell, k (nmol,natoms); thole_u (nmol,natoms,natoms)."""
-    r = torch.as_tensor(np.asarray(r_core, dtype=np.float64))
+    r = r_core if isinstance(r_core, torch.Tensor) else torch.as_tensor(np.asarray(r_core, dtype=np.float64))
     D = D if isinstance(D, torch.Tensor) else torch.as_tensor(np.asarray(D, dtype=np.float64))
     nmol, natoms = r.shape[0], r.shape[1]
     D = D.reshape(nmol, natoms, 3)
@@ -137,8 +137,9 @@ def u_ind_pbc(r_core, D, q_core, q_shell, k, thole_u, box, kappa, nmax=None, ima
     X_0 = torch.cat([rf, rf[pol_t]], 0)
     e_d = ewald_energy(X_d, Q, M, box, kappa, nmax, images)
     e_0 = ewald_energy(X_0, Q, M, box, kappa, nmax, images)
-    R, qis, qjs, _, _, u, kk = uind_dense.dense_inputs(r_core, q_core, q_shell, k, thole_u)
-    R, qis, qjs, kk = (uind_dense._t(a) for a in (R, qis, qjs, kk))
+    _, qis, qjs, _, _, u, kk = uind_dense.dense_inputs(r.detach().numpy(), q_core, q_shell, k, thole_u)
+    R = r[None, :, None, :, :] - r[:, None, :, None, :]            # inside the graph: differentiable in r as well
+    qis, qjs, kk = (uind_dense._t(a) for a in (qis, qjs, kk))
     u = uind_dense._t(u) if not np.isscalar(u) else torch.tensor(float(u), dtype=_F64)
     return (e_d - e_0) + _thole_intra(R, D, qis, qjs, u) + uind_dense.spring_energy(D, kk)
 
@@ -148,6 +149,14 @@ def u_ind_pbc_and_grad(r_core, D, q_core, q_shell, k, thole_u, box, kappa, nmax=
     e = u_ind_pbc(r_core, Dt, q_core, q_shell, k, thole_u, box, kappa, nmax, images)
     (g,) = torch.autograd.grad(e, Dt)
     return float(e.detach()), g.detach().numpy().reshape(np.asarray(D).shape)
+
+
+def u_ind_pbc_core_grad(r_core, D, q_core, q_shell, k, thole_u, box, kappa, nmax=None, images=1):
+    """dU_ind/dr_core at fixed displacements (the shells move with their cores)."""
+    rt = torch.as_tensor(np.asarray(r_core, dtype=np.float64)).clone().requires_grad_(True)
+    e = u_ind_pbc(rt, D, q_core, q_shell, k, thole_u, box, kappa, nmax, images)
+    (g,) = torch.autograd.grad(e, rt)
+    return g.detach().numpy()
 
 
 def default_kappa(box):

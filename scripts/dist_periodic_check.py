@@ -28,9 +28,11 @@ for name, maker, nx, density, p2p in (("water", synth.water_box, 6, 33.4, True),
     dE = abs(float(e2[0]) - float(e1[0])) / abs(float(e1[0]))
     dg = float((g2 - g1).abs().max() / g1.abs().max())
     dm = abs(i2["U_ind"] - i1["U_ind"]) / abs(i1["U_ind"])
-    ok = dE < 1e-11 and dg < 1e-12 and dm < 1e-10 and i1["flags"] == 0 and i2["flags"] == 0
+    c1 = full.core_gradient(D); c2 = sh.core_gradient(D)
+    dc = float((c2 - c1).abs().max() / c1.abs().max())
+    ok = dE < 1e-11 and dg < 1e-12 and dm < 1e-10 and dc < 1e-11 and i1["flags"] == 0 and i2["flags"] == 0
     bad += not ok
-    print(f"rank {rank}/{world} {name} {nmol}: dE {dE:.1e} dg {dg:.1e} dUmin {dm:.1e} iterations {i1['iterations']}/{i2['iterations']} "
+    print(f"rank {rank}/{world} {name} {nmol}: dE {dE:.1e} dg {dg:.1e} dUmin {dm:.1e} dcore {dc:.1e} iterations {i1['iterations']}/{i2['iterations']} "
           f"flags {i1['flags']}/{i2['flags']} minimise {t_full*1e3:.1f} ms on 1 GPU, {t_sh*1e3:.1f} ms sharded {'OK' if ok else 'FAIL'}", flush=True)
     sh.close(); full.close()
 dist.barrier(); dist.destroy_process_group()

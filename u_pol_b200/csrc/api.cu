@@ -407,7 +407,7 @@ static int upol_system_set_periodic_impl(upol_system *s, const double *box, doub
 }
 
 static int upol_uind_core_gradient_dev_impl(upol_system *s, const double *d, double *dudr, void *stream) {
-    if (!s || !d || !dudr || s->ewald) return UPOL_ERR_ARG;     // open boundaries only
+    if (!s || !d || !dudr) return UPOL_ERR_ARG;
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = sys_gather_d(s, d, s->dc, st);

@@ -211,6 +211,7 @@ void ewald_free(upol_system *s);
 void ewald_invalidate(upol_system *s);
 int ewald_static_part(upol_system *s, PairArgs a, int *n_slots, cudaStream_t st);
 int ewald_dynamic_part(upol_system *s, PairArgs a, int *n_slots, cudaStream_t st);
+int ewald_field_part(upol_system *s, PairArgs a, int which, int *n_slots, cudaStream_t st);
 
 // minimiser (minimize.cu)
 int minimize_compact(upol_system *s, double *d_compact, const upol_min_options *o,

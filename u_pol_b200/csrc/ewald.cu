@@ -35,6 +35,8 @@ struct EwaldState {
     double2 *Sc = nullptr;     // [nk_pad] structure factor of the cores (charge qc)
     double2 *Ss0 = nullptr;    // [nk_pad] ... of the shells sitting on their cores (d = 0)
     double2 *Ssd = nullptr;    // [nk_pad] ... of the shells at r - d
+    double2 *Sstat = nullptr;  // [nk_pad] Sc + Ss0 / 2 (static columns, core-force pass)
+    double2 *Szero = nullptr;  // [nk_pad] zeros
     double4 *cols0 = nullptr;  // [nb_pad] shells at their cores: x, y, z, qs
     double2 *rec = nullptr;    // [3 * max(na_pad, nb_pad)] per-charge records of the structure-factor pass
     double2 *partial = nullptr;  // [kSfacChunks][nk_pad] per-chunk partial structure factors
@@ -261,7 +263,8 @@ template <bool STATIC>
 __global__ void __launch_bounds__(128)
 ewald_rows_kernel(const PairArgs a, const EwaldArgs w, int nk_pad, const int4 *__restrict__ kn,
                   const double *__restrict__ kA, const double2 *__restrict__ Sc, const double2 *__restrict__ Ss,
-                  const double4 *__restrict__ cols, const double4 *__restrict__ cols_static, int na_pad, int slot0) {
+                  const double4 *__restrict__ cols, const double4 *__restrict__ cols_static, int na_pad, int slot0,
+                  bool with_b) {
     __shared__ double4 s_h[128 / kRun];          // per run: nx, ny, first nz
     __shared__ double s_A[128];
     __shared__ double2 s_c[128], s_s[128];
@@ -339,7 +342,7 @@ ewald_rows_kernel(const PairArgs a, const EwaldArgs w, int nk_pad, const int4 *_
                 pa -= c.w * g;
                 gx -= c.w * cc * x; gy -= c.w * cc * y; gz -= c.w * cc * z;
             }
-            const int loB = a.exB_lo[i], lenB = a.exB_len[i], own = na_pad + i;
+            const int loB = a.exB_lo[i], lenB = with_b ? a.exB_len[i] : 0, own = na_pad + i;
             for (int b = loB; b < loB + lenB; ++b) {
                 if (b == own) continue;
                 const double4 c = cols[b];
@@ -361,6 +364,12 @@ ewald_rows_kernel(const PairArgs a, const EwaldArgs w, int nk_pad, const int4 *_
             out[2 * a.part_stride + lr] = gx; out[3 * a.part_stride + lr] = gy; out[4 * a.part_stride + lr] = gz;
         }
     }
+}
+
+__global__ void ewald_sstat_kernel(int nk_pad, const double2 *__restrict__ Sc, const double2 *__restrict__ Ss0,
+                                   double2 *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nk_pad) out[k] = make_double2(Sc[k].x + 0.5 * Ss0[k].x, Sc[k].y + 0.5 * Ss0[k].y);
 }
 
 inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
@@ -390,7 +399,7 @@ void choose_slots(const upol_system *s, const EwaldState *e, int n_rows, int n_t
 void ewald_free(upol_system *s) {
     EwaldState *e = static_cast<EwaldState *>(s->ewald);
     if (!e) return;
-    void *ptrs[] = {e->kn, e->kA, e->Sc, e->Ss0, e->Ssd, e->cols0, e->rec, e->partial, e->mol_site0, e->mol_nsite, e->bad};
+    void *ptrs[] = {e->kn, e->kA, e->Sc, e->Ss0, e->Ssd, e->Sstat, e->Szero, e->cols0, e->rec, e->partial, e->mol_site0, e->mol_nsite, e->bad};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete e;
     s->ewald = nullptr;
@@ -455,6 +464,8 @@ int ewald_setup(upol_system *s, const double *box, double kappa, int nmax) {
         cudaMalloc((void **)&e->Sc, sizeof(double2) * e->nk_pad) != cudaSuccess ||
         cudaMalloc((void **)&e->Ss0, sizeof(double2) * e->nk_pad) != cudaSuccess ||
         cudaMalloc((void **)&e->Ssd, sizeof(double2) * e->nk_pad) != cudaSuccess ||
+        cudaMalloc((void **)&e->Sstat, sizeof(double2) * e->nk_pad) != cudaSuccess ||
+        cudaMalloc((void **)&e->Szero, sizeof(double2) * e->nk_pad) != cudaSuccess ||
         cudaMalloc((void **)&e->cols0, sizeof(double4) * std::max<int64_t>(s->nb_pad, 1)) != cudaSuccess ||
         cudaMalloc((void **)&e->rec, sizeof(double2) * 3 * std::max<int64_t>(std::max(s->na_pad, s->nb_pad), 1)) != cudaSuccess ||
         cudaMalloc((void **)&e->partial, sizeof(double2) * (size_t)kSfacChunks * e->nk_pad) != cudaSuccess ||
@@ -464,7 +475,8 @@ int ewald_setup(upol_system *s, const double *box, double kappa, int nmax) {
         cudaGetLastError();
         return fail(UPOL_ERR_ALLOC);
     }
-    if (cudaMemcpy(e->kn, kn.data(), sizeof(int4) * e->nk_pad, cudaMemcpyHostToDevice) != cudaSuccess ||
+    if (cudaMemset(e->Szero, 0, sizeof(double2) * e->nk_pad) != cudaSuccess ||
+        cudaMemcpy(e->kn, kn.data(), sizeof(int4) * e->nk_pad, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(e->kA, kA.data(), sizeof(double) * e->nk_pad, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(e->mol_site0, s->h_mol_site0.data(), sizeof(int) * s->nmol, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(e->mol_nsite, s->h_mol_nsite.data(), sizeof(int) * s->nmol, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -536,7 +548,7 @@ int ewald_static_part(upol_system *s, PairArgs a, int *n_slots, cudaStream_t st)
     ewald_real_kernel<true><<<g1, kBlock, 0, st>>>(a, w);
     dim3 g2(nblk(a.n_rows, 128), (unsigned)s_rec);
     ewald_rows_kernel<true><<<g2, 128, 0, st>>>(a, w, e->nk_pad, e->kn, e->kA, e->Sc, e->Ss0, s->cols, s->cols_static,
-                                                (int)s->na_pad, s_real);
+                                                (int)s->na_pad, s_real, true);
     UPOL_CUDA(cudaGetLastError());
     *n_slots = s_real + s_rec;
     return UPOL_OK;
@@ -558,7 +570,33 @@ int ewald_dynamic_part(upol_system *s, PairArgs a, int *n_slots, cudaStream_t st
     ewald_real_kernel<false><<<g1, kBlock, 0, st>>>(a, w);
     dim3 g2(nblk(a.n_rows, 128), (unsigned)s_rec);
     ewald_rows_kernel<false><<<g2, 128, 0, st>>>(a, w, e->nk_pad, e->kn, e->kA, e->Sc, e->Ssd, s->cols, s->cols_static,
-                                                 (int)s->na_pad, s_real);
+                                                 (int)s->na_pad, s_real, true);
+    UPOL_CUDA(cudaGetLastError());
+    *n_slots = s_real + s_rec;
+    return UPOL_OK;
+}
+
+// Core-force pass: field (comps 2-4 of part[0 .. *n_slots)) at the rows of `a` from ONE column set
+// (a.cols, a.n_tiles tiles, excluded interval a.exA_*), whose structure factor is `which`:
+// 0 shells at r - d, 1 shells on their cores, 2 static columns (qc + qs/2 on the cores).
+int ewald_field_part(upol_system *s, PairArgs a, int which, int *n_slots, cudaStream_t st) {
+    EwaldState *e = static_cast<EwaldState *>(s->ewald);
+    const EwaldArgs w = make_args(e);
+    int rc = ewald_static_sfac(s, e, w, st);
+    if (rc) return rc;
+    const double2 *S = which == 0 ? e->Ssd : which == 1 ? e->Ss0 : e->Sstat;
+    if (which == 2) ewald_sstat_kernel<<<nblk(e->nk_pad, 256), 256, 0, st>>>(e->nk_pad, e->Sc, e->Ss0, e->Sstat);
+    a.n_tiles_a = a.n_tiles;                          // a single section
+    a.exB_lo = a.exA_lo; a.exB_len = a.exA_len;       // never read: no B tiles, with_b = false
+    a.gate = nullptr;
+    int s_real, s_rec;
+    choose_slots(s, e, a.n_rows, a.n_tiles, a.part_stride, s_real, s_rec);
+    a.n_split = s_real;
+    dim3 g1(nblk(a.n_rows, kBlock), (unsigned)s_real);
+    ewald_real_kernel<false><<<g1, kBlock, 0, st>>>(a, w);
+    dim3 g2(nblk(a.n_rows, 128), (unsigned)s_rec);
+    ewald_rows_kernel<false><<<g2, 128, 0, st>>>(a, w, e->nk_pad, e->kn, e->kA, S, e->Szero, static_cast<const double4 *>(a.cols),
+                                                 s->cols_static, 0, s_real, false);
     UPOL_CUDA(cudaGetLastError());
     *n_slots = s_real + s_rec;
     return UPOL_OK;

@@ -732,6 +732,53 @@ int sys_core_forces(upol_system *s, const double *dcmp, double *dudr, cudaStream
         s->inv_grid, s->mix_slot, s->rowx, s->rowy, s->rowz, s->cols + s->na_pad, s->cols_f);
     build_force_tables_kernel<<<nblk(std::max<int64_t>(n, s->nb_pad), 256), 256, 0, st>>>(
         (int)n, (int)nd, (int)s->nb_pad, s->r, s->row_site, s->row_qs, s->site_x, s->site_y, s->site_z, s->cols_dcore);
+    if (s->ewald) {
+        // periodic box: the same four fields from the Ewald kernels (ewald.cu), one column set at a time
+        int slots = 0, rc = UPOL_OK;
+        if (nr > 0) {
+            const int nbf = (int)nblk(nr, kFinRows);
+            PairArgs a = base_args(s);
+            a.rx = s->rowx; a.ry = s->rowy; a.rz = s->rowz;
+            a.cols = s->cols; a.n_tiles = (int)((s->na_pad + s->nb_pad) / kTileCols);
+            rc = ewald_dynamic_part(s, a, &slots, st);                       // F (also refreshes S of the shells)
+            if (rc) return rc;
+            fold_fields_kernel<3><<<nbf, kFinBlock, 0, st>>>((int)nr, (int)r_lo, nd, slots, s->part, a.part_stride, 2, F);
+            a = base_args(s);
+            a.rx = s->srowx; a.ry = s->srowy; a.rz = s->srowz;
+            a.cols = s->cols_static; a.n_tiles = a.n_tiles_a;
+            rc = ewald_field_part(s, a, 2, &slots, st);                      // H
+            if (rc) return rc;
+            fold_fields_kernel<3><<<nbf, kFinBlock, 0, st>>>((int)nr, (int)r_lo, nd, slots, s->part, a.part_stride, 2, H);
+        }
+        if (ns > 0) {
+            if (nr == 0) {                                                   // S of the shells is still needed
+                PairArgs a0 = base_args(s);
+                a0.rx = s->rowx; a0.ry = s->rowy; a0.rz = s->rowz; a0.cols = s->cols;
+                a0.n_tiles = (int)((s->na_pad + s->nb_pad) / kTileCols);
+                rc = ewald_dynamic_part(s, a0, &slots, st);
+                if (rc) return rc;
+            }
+            PairArgs a = base_args(s);
+            a.n_rows = (int)ns; a.row0 = (int)s_lo; a.part_stride = part_stride_for(ns);
+            a.rx = s->site_x; a.ry = s->site_y; a.rz = s->site_z;
+            a.exA_lo = s->exS_lo; a.exA_len = s->exS_len;
+            a.n_tiles = (int)(s->nb_pad / kTileCols);
+            a.cols = s->cols + s->na_pad;
+            rc = ewald_field_part(s, a, 0, &slots, st);                      // G: shells at r - d
+            if (rc) return rc;
+            fold_fields_kernel<3><<<nblk(ns, kFinRows), kFinBlock, 0, st>>>((int)ns, (int)s_lo, n, slots, s->part, a.part_stride, 2, GH);
+            a.cols = s->cols_dcore;
+            rc = ewald_field_part(s, a, 1, &slots, st);                      // H': Drude cores
+            if (rc) return rc;
+            fold_fields_kernel<3><<<nblk(ns, kFinRows), kFinBlock, 0, st>>>((int)ns, (int)s_lo, n, slots, s->part, a.part_stride, 2, GH + 3 * n);
+            core_force_assemble_kernel<<<nblk(ns, 128), 128, 0, st>>>((int)s_lo, (int)s_hi, (int)n, (int)nd, s->r, dcmp, s->qc, s->qs,
+                                                                     s->site_row, s->row_site, s->row_qs, s->th_ptr, s->th_row,
+                                                                     s->th_u, F, H, GH, dudr);
+        }
+        UPOL_CUDA(cudaGetLastError());
+        if (s->nranks > 1) return comm_allgather_sites(s, dudr, st);
+        return UPOL_OK;
+    }
     if (nr > 0) {
         const int nbf = (int)nblk(nr, kFinRows);
         {   // F: field at the shells (main pass, field only)

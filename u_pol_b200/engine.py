@@ -257,7 +257,7 @@ class UindSystem:
         minimiser then refer to the periodic system (direct Ewald sum, tin-foil; definition and checker:
         ``oracle/ewald_dense.py``).  ``kappa`` defaults to 13 / min(box); ``nmax`` > 0 replaces the default
         reciprocal cut-off exp(-k^2/4kappa^2) >= exp(-41.5) by the cube |n| <= nmax.  fp64; works with row
-        shards (``attach_process_group``) like the open-boundary path."""
+        shards (``attach_process_group``) and ``core_gradient`` like the open-boundary path."""
         if box is None:
             L.check(L.lib().upol_system_set_periodic(self._h, None, 0.0, 0), "upol_system_set_periodic")
             return None
