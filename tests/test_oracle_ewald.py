@@ -88,3 +88,22 @@ def test_periodic_uind_kappa_independent_and_gradient_consistent():
     R, qis, qjs, qic, qjc, u, kk = uind_dense.dense_inputs(s.r_core, s.q_core, s.q_shell, s.k, s.thole_u)
     e_open = float(uind_dense.u_ind(R, D, qis, qjs, qic, qjc, u, kk))
     assert abs(e_open - e0) > 1e-4 * abs(e0)
+
+
+def test_periodic_core_gradient_of_the_oracle():
+    """dU_ind/dr_core under a box: no net force, agrees with central differences, kappa independent."""
+    s = synth.water_box(6, seed=9)
+    D = synth.random_displacements(s, seed=10)
+    box = np.ptp(s.r_core.reshape(-1, 3), axis=0) + np.array([0.5, 0.6, 0.7])
+    k0 = ewald_dense.default_kappa(box)
+    args = (s.q_core, s.q_shell, s.k, s.thole_u, box)
+    g = ewald_dense.u_ind_pbc_core_grad(s.r_core, D, *args, k0)
+    assert np.abs(g.reshape(-1, 3).sum(0)).max() <= 1e-9 * np.abs(g).max()
+    g2 = ewald_dense.u_ind_pbc_core_grad(s.r_core, D, *args, 1.2 * k0, images=2)
+    assert np.abs(g - g2).max() <= 1e-9 * np.abs(g).max()
+    rng = np.random.default_rng(1)
+    v = rng.normal(size=s.r_core.shape)
+    h = 1e-6
+    ep = float(ewald_dense.u_ind_pbc(s.r_core + h * v, D, *args, k0))
+    em = float(ewald_dense.u_ind_pbc(s.r_core - h * v, D, *args, k0))
+    assert (ep - em) / (2 * h) == pytest.approx(float((g * v).sum()), rel=1e-5)
