@@ -119,10 +119,11 @@ def test_random_boxes_vs_oracle(maker, nmol, seed):
     # host-buffer entry point gives the same numbers
     eh, gh = sys_.energy_grad_host(D)
     assert eh[0] == float(e[0]) and np.array_equal(gh, g.cpu().numpy())
-    # mixed precision: energies are always fp64 (and then the field comes from the same fp64 pass);
-    # the fp32 field kernel serves field-only calls
-    em, _ = sys_.energy_grad(D, precision="mixed")
+    # mixed precision: energy AND gradient from one fp32 pass in difference form (pair_diff.cu) ...
+    em, gme = sys_.energy_grad(D, precision="mixed")
     assert abs(float(em[0]) - e_ref) <= RTOL_MIXED * abs(e_ref)
+    assert np.abs(gme.cpu().numpy().reshape(g_ref.shape) - g_ref).max() <= RTOL_MIXED * np.abs(g_ref).max()
+    # ... and the field-only variant a minimiser iteration runs
     _, gm = sys_.energy_grad(D, precision="mixed", want_energy=False)
     assert np.abs(gm.cpu().numpy().reshape(g_ref.shape) - g_ref).max() <= RTOL_MIXED * np.abs(g_ref).max()
     assert np.linalg.norm(gm.cpu().numpy().reshape(g_ref.shape) - g_ref) <= RTOL_MIXED * np.linalg.norm(g_ref)
@@ -150,6 +151,56 @@ def test_zero_distance_and_padding_sites():
     Rij, Qis, Qjs, Qic, Qjc, u, k = _dense(s2)
     e_ref, _ = uind_dense.u_ind_and_grad(Rij, D2, Qis, Qjs, Qic, Qjc, u, k)
     assert abs(float(e2[0]) - e_ref) <= RTOL_FP64 * abs(e_ref) + 1e-14 * _sum_abs_terms(s2)
+    # the fp32 difference-form kernel meets 1/0 in those tiles and has to redo them with the predicated loop
+    em, gm = UindSystem.from_drude_system(s2).energy_grad(D2, precision="mixed")
+    assert abs(float(em[0]) - e_ref) <= RTOL_MIXED * abs(e_ref)
+    assert np.abs(gm.cpu().numpy().reshape(s.nmol, 5, 3) - g2).max() <= RTOL_MIXED * np.abs(g2).max()
+    assert torch.isfinite(gm).all()
+
+
+def test_mixed_drops_zero_distance_terms_like_the_reference():
+    """A CHARGED site of one molecule exactly on a core (R = 0) or on a shell (A = 0) of another one: the
+    reference drops the zero-distance term and keeps everything else (polarization.py:33-42).  The fp32
+    difference-form kernel must do the same, term by term (f(A), f(R), f(C) are dropped one by one)."""
+    s = synth.water_box(8, seed=6)
+    D = synth.random_displacements(s, seed=10)
+    for case in ("R", "A"):
+        r = s.r_core.copy()
+        if case == "R":
+            r[1, 1] = r[0, 0]                    # H1 of molecule 1 on the O core of molecule 0
+            special = [0]
+        else:
+            r[2, 2] = r[3, 0] - D[3, 0]          # H2 of molecule 2 on the O shell of molecule 3
+            special = [3]
+        s2 = DrudeSystem(r_core=r, q_core=s.q_core, q_shell=s.q_shell, alpha=s.alpha, thole_u=s.thole_u, site_names=[])
+        sys_ = UindSystem.from_drude_system(s2)
+        e64, g64 = sys_.energy_grad(D)
+        em, gm = sys_.energy_grad(D, precision="mixed")
+        assert torch.isfinite(em).all() and torch.isfinite(gm).all()
+        if case == "R":                          # exact zero for the dense oracle as well
+            Rij, Qis, Qjs, Qic, Qjc, u, k = _dense(s2)
+            e_ref, _ = uind_dense.u_ind_and_grad(Rij, D, Qis, Qjs, Qic, Qjc, u, k)
+            assert abs(float(e64[0]) - e_ref) <= 1e-9 * abs(e_ref)
+        assert abs(float(em[0]) - float(e64[0])) <= RTOL_MIXED * abs(float(e64[0]))
+        g64 = g64.cpu().numpy().reshape(D.shape); gm = gm.cpu().numpy().reshape(D.shape)
+        keep = np.ones(s.nmol, bool); keep[special] = False
+        assert np.abs(gm[keep] - g64[keep]).max() <= RTOL_MIXED * np.abs(g64[keep]).max()
+        assert np.abs(gm[special] - g64[special]).max() <= RTOL_MIXED * np.abs(g64[special]).max()
+
+
+@pytest.mark.parametrize("name", REF_SYSTEMS)
+@pytest.mark.parametrize("dset", DSETS)
+def test_mixed_energy_and_grad_vs_reference_source(ref_exec, name, dset):
+    """UPOL_MIXED: energy and gradient from ONE fp32 difference-form pass (no fp64 pair kernel), against
+    the outputs of the reference's own Uind + reverse-mode AD; north-star bar 1e-5."""
+    s = _load(ref_exec, name)
+    D = ref_exec[f"{name}/{dset}/D"]
+    e_ref, g_ref = float(ref_exec[f"{name}/{dset}/Uind"]), ref_exec[f"{name}/{dset}/grad"]
+    e, g = UindSystem.from_drude_system(s).energy_grad(D, precision="mixed")
+    assert abs(float(e[0]) - e_ref) <= RTOL_MIXED * abs(e_ref) + 1e-14 * _sum_abs_terms(s)
+    g = g.cpu().numpy().reshape(g_ref.shape)
+    assert np.abs(g - g_ref).max() <= RTOL_MIXED * np.abs(g_ref).max()
+    assert np.all(g[s.q_shell == 0] == 0.0)
 
 
 def test_gradient_finite_difference():
@@ -211,6 +262,12 @@ def test_config3_size_vs_c_oracle():
     gm = sys_.energy_grad(D, precision="mixed", want_energy=False)[1].cpu().numpy().reshape(g_ref.shape)
     assert np.linalg.norm(gm - g_ref) <= RTOL_MIXED * np.linalg.norm(g_ref)
     assert np.abs(gm - g_ref).max() <= RTOL_MIXED * np.abs(g_ref).max()
+    # mixed energy + gradient in one call (difference form), against the 80-bit arbiter and the C oracle
+    em, gme = sys_.energy_grad(D, precision="mixed")
+    assert abs(float(em[0]) - e_ld) <= RTOL_MIXED * abs(e_ld)
+    assert abs(float(em[1]) - float(e[1])) <= RTOL_MIXED * abs(float(e[1]))    # the inter-molecular part on its own
+    gme = gme.cpu().numpy().reshape(g_ref.shape)
+    assert np.abs(gme - g_ref).max() <= RTOL_MIXED * np.abs(g_ref).max()
 
 
 def test_full_size_100k_drudes_properties():
@@ -254,3 +311,8 @@ def test_full_size_100k_drudes_properties():
     gm = sys_.energy_grad(D, precision="mixed", want_energy=False)[1].cpu().numpy().reshape(D.shape)
     assert np.linalg.norm(gm - g) <= RTOL_MIXED * np.linalg.norm(g)
     assert np.abs(gm - g).max() <= RTOL_MIXED * np.abs(g).max()
+    # (5) mixed energy + gradient in one call
+    em, gme = sys_.energy_grad(D, precision="mixed")
+    assert abs(float(em[0]) - float(e[0])) <= RTOL_MIXED * abs(float(e[0]))
+    assert abs(float(em[1]) - float(e[1])) <= RTOL_MIXED * abs(float(e[1]))
+    assert np.abs(gme.cpu().numpy().reshape(D.shape) - g).max() <= RTOL_MIXED * np.abs(g).max()

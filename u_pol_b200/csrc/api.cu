@@ -43,7 +43,8 @@ void free_system(upol_system *s) {
                     s->exB_lo, s->exB_len, s->rowx, s->rowy, s->rowz, s->srowx, s->srowy, s->srowz,
                     s->cols, s->cols_f, s->mix_slot, s->exM_lo, s->exM_len, s->cols_static, s->th_ptr, s->th_row, s->th_u, s->part, s->dc,
                     s->gc, s->eblock, s->energy, s->e_static, s->phi_static, s->site_row,
-                    s->cols_dcore, s->site_x, s->exS_lo, s->cf_tmp};
+                    s->cols_dcore, s->site_x, s->exS_lo, s->cf_tmp,
+                    s->cols_x, s->cols_d, s->cols_d2, s->site_nslot, s->exP_lo, s->exP_len, s->exN_lo, s->exN_len};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (s->pin) cudaFreeHost(s->pin);
     if (s->hscratch) cudaFree(s->hscratch);
@@ -139,6 +140,7 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
     s->na_pad = round_up(nsite, kTileCols);
     s->nb_pad = round_up(std::max<int64_t>(s->nd, 1), kTileCols);
     s->nm_pad = round_up(nsite + s->nd, kTileCols);
+    s->nn_pad = round_up(std::max<int64_t>(nsite - s->nd, 1), kTileCols);
     s->mol_lo = 0; s->mol_hi = s->nmol; s->row_lo = 0; s->row_hi = s->nd;
 
     // per-row tables
@@ -146,9 +148,24 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
     std::vector<double> row_qs(std::max<int64_t>(s->nd, 1), 0.0), row_k(std::max<int64_t>(s->nd, 1), 0.0);
     std::vector<int32_t> mix_slot(nsite), exM_lo(s->nd_pad, 0), exM_len(s->nd_pad, 0);
     for (int64_t i = 0, slot = 0; i < nsite; ++i) { mix_slot[i] = (int32_t)slot; slot += (s->h_site_row[i] >= 0) ? 2 : 1; }
+    // difference-form mixed kernel: non-polarisable sites get slots of section N in site order
+    std::vector<int32_t> site_nslot(nsite, -1), mol_n0(s->nmol, 0), mol_nn(s->nmol, 0);
+    {
+        int32_t slot = 0;
+        for (int64_t i = 0; i < nsite; ++i) {
+            const int m = site_mol[i];
+            if (i == s->h_mol_site0[m]) mol_n0[m] = slot;
+            if (s->h_site_row[i] < 0) { site_nslot[i] = slot++; mol_nn[m]++; }
+        }
+    }
+    std::vector<int32_t> exP_lo(s->nd_pad, 0), exP_len(s->nd_pad, 0), exN_lo(s->nd_pad, 0), exN_len(s->nd_pad, 0);
     for (int64_t i = 0; i < s->nd; ++i) {
         const int site = s->h_drude_site[i];
         const int m = site_mol[site];
+        exP_lo[i] = s->h_mol_row0[m];
+        exP_len[i] = s->h_mol_nrow[m];
+        exN_lo[i] = (int32_t)s->nb_pad + mol_n0[m];              // concatenated column index
+        exN_len[i] = mol_nn[m];
         exM_lo[i] = mix_slot[s->h_mol_site0[m]];
         exM_len[i] = s->h_mol_nsite[m] + s->h_mol_nrow[m];
         exA_lo[i] = s->h_mol_site0[m];
@@ -203,6 +220,10 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
     TRY(dev_alloc(&s->cols_f, s->nm_pad));
     TRY(dev_alloc(&s->mix_slot, nsite)); TRY(dev_alloc(&s->exM_lo, s->nd_pad)); TRY(dev_alloc(&s->exM_len, s->nd_pad));
     TRY(dev_alloc(&s->cols_static, s->na_pad));
+    TRY(dev_alloc(&s->cols_x, s->nb_pad + s->nn_pad)); TRY(dev_alloc(&s->cols_d, s->nb_pad)); TRY(dev_alloc(&s->cols_d2, s->nb_pad));
+    TRY(dev_alloc(&s->site_nslot, nsite));
+    TRY(dev_alloc(&s->exP_lo, s->nd_pad)); TRY(dev_alloc(&s->exP_len, s->nd_pad));
+    TRY(dev_alloc(&s->exN_lo, s->nd_pad)); TRY(dev_alloc(&s->exN_len, s->nd_pad));
     TRY(dev_alloc(&s->th_ptr, s->nd + 1)); TRY(dev_alloc(&s->th_row, th_row.size())); TRY(dev_alloc(&s->th_u, th_u.size()));
     TRY(dev_alloc(&s->part, part_elems));
     s->part_elems = part_elems;
@@ -231,6 +252,11 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
         cp(s->mix_slot, mix_slot.data(), sizeof(int32_t) * nsite);
         cp(s->exM_lo, exM_lo.data(), sizeof(int32_t) * s->nd_pad);
         cp(s->exM_len, exM_len.data(), sizeof(int32_t) * s->nd_pad);
+        cp(s->site_nslot, site_nslot.data(), sizeof(int32_t) * nsite);
+        cp(s->exP_lo, exP_lo.data(), sizeof(int32_t) * s->nd_pad);
+        cp(s->exP_len, exP_len.data(), sizeof(int32_t) * s->nd_pad);
+        cp(s->exN_lo, exN_lo.data(), sizeof(int32_t) * s->nd_pad);
+        cp(s->exN_len, exN_len.data(), sizeof(int32_t) * s->nd_pad);
         cp(s->th_ptr, th_ptr.data(), sizeof(int32_t) * (s->nd + 1));
         cp(s->th_row, th_row.data(), sizeof(int32_t) * th_row.size());
         cp(s->th_u, th_u.data(), sizeof(double) * th_u.size());

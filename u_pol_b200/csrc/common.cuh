@@ -58,6 +58,11 @@ struct PairArgs {
     int64_t part_stride;
     // mixed mode only: box centre and 1/grid of the fixed-point coordinates
     double cx, cy, cz, inv_grid;
+    // mixed mode (pair_diff.cu): row displacements [nd*3] (compact), per-site -2 d_j | q_shell (float4) and
+    // |d_j|^2 (float) of section P
+    const double *dcomp;
+    const void *cols_d;
+    const float *cols_d2;
     // device-side gate (minimiser): the kernel returns at once when (*gate & gate_skip_mask) != 0
     const int *gate;
     int gate_skip_mask;
@@ -70,6 +75,8 @@ constexpr int kMaxPack = 17 * 8;   // (max history + 1) x values per slot of the
 
 int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, cudaStream_t st);
 int launch_pair_mixed(const PairArgs &a, cudaStream_t st);
+int launch_pair_diff(const PairArgs &a, bool with_pot, cudaStream_t st);
+int diff_rows_per_block();
 int launch_pair_static(const PairArgs &a, cudaStream_t st);
 int launch_pair_fp64_two_fields(const PairArgs &a, cudaStream_t st);
 int fp64_rows_per_block();
@@ -107,6 +114,14 @@ struct upol_system {
     int *mix_slot = nullptr;      // [nsite] column slot of a site's core in cols_f (its shell is slot+1)
     int *exM_lo = nullptr, *exM_len = nullptr;   // [nd_pad] excluded interval of a row in cols_f
     int64_t nm_pad = 0;
+    // mixed mode, difference form (pair_diff.cu): section P = polarisable sites in Drude-row order (nb_pad
+    // slots), section N = the other sites (nn_pad slots)
+    int4 *cols_x = nullptr;       // [nb_pad + nn_pad] fixed-point core position, float bits of q_core
+    float4 *cols_d = nullptr;     // [nb_pad] -2 d_j in grid units, q_shell
+    float *cols_d2 = nullptr;     // [nb_pad] |d_j|^2 in grid units^2
+    int *site_nslot = nullptr;    // [nsite] slot of a non-polarisable site in section N, -1 otherwise
+    int *exP_lo = nullptr, *exP_len = nullptr, *exN_lo = nullptr, *exN_len = nullptr;   // [nd_pad]
+    int64_t nn_pad = 0;
     double4 *cols_static = nullptr;  // [na_pad] cores, CENTRED coordinates, q = qc + qs/2 (static pass)
     double centre[3] = {0, 0, 0};
     double inv_grid = 1.0;        // fixed-point grid: 1/grid, grid = 2^-k nm so the box fits +-2^30

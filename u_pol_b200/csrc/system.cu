@@ -53,6 +53,22 @@ __global__ void build_core_columns_kernel(int nsite, int na_pad, const double *_
     }
 }
 
+// Mixed mode, difference form: fixed-point core columns, section P (polarisable sites, Drude-row order)
+// then section N (the others); once per geometry.
+__global__ void build_diff_columns_kernel(int nsite, int nd, int nb_pad, int nn_pad, const double *__restrict__ r,
+                                          const double *__restrict__ qc, const int *__restrict__ site_row,
+                                          const int *__restrict__ site_nslot, double cx, double cy, double cz,
+                                          double inv_grid, int4 *__restrict__ cols_x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_n = nsite - nd;
+    if (i >= nd && i < nb_pad) cols_x[i] = make_int4(kFixFar, kFixFar, kFixFar, 0);                      // P padding
+    if (i >= n_n && i < nn_pad) cols_x[nb_pad + i] = make_int4(kFixFar, kFixFar, kFixFar, 0);            // N padding
+    if (i >= nsite) return;
+    const int row = site_row[i];
+    const int slot = row >= 0 ? row : nb_pad + site_nslot[i];
+    cols_x[slot] = fix_col(r[3 * i] - cx, r[3 * i + 1] - cy, r[3 * i + 2] - cz, inv_grid, qc[i]);
+}
+
 __global__ void build_static_rows_kernel(int nd, const int *__restrict__ row_site, const double *__restrict__ r,
                                          double *__restrict__ sx, double *__restrict__ sy, double *__restrict__ sz) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,7 +84,8 @@ __global__ void prepare_shells_kernel(int nd, int nb_pad, const int *__restrict_
                                       double cx, double cy, double cz, double inv_grid,
                                       const int *__restrict__ mix_slot,
                                       double *__restrict__ rowx, double *__restrict__ rowy, double *__restrict__ rowz,
-                                      double4 *__restrict__ colsB, int4 *__restrict__ cols_f) {
+                                      double4 *__restrict__ colsB, int4 *__restrict__ cols_f,
+                                      float4 *__restrict__ cols_d, float *__restrict__ cols_d2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb_pad) return;
     if (i < nd) {
@@ -77,8 +94,14 @@ __global__ void prepare_shells_kernel(int nd, int nb_pad, const int *__restrict_
         rowx[i] = x; rowy[i] = y; rowz[i] = z;
         colsB[i] = make_double4(x, y, z, row_qs[i]);
         cols_f[mix_slot[s] + 1] = fix_col(x - cx, y - cy, z - cz, inv_grid, row_qs[i]);
+        // difference-form mixed kernel: -2 d_j and |d_j|^2 in grid units, from the SAME fp32 values
+        const float dx = (float)(dc[3 * i] * inv_grid), dy = (float)(dc[3 * i + 1] * inv_grid), dz = (float)(dc[3 * i + 2] * inv_grid);
+        cols_d[i] = make_float4(-2.0f * dx, -2.0f * dy, -2.0f * dz, (float)row_qs[i]);
+        cols_d2[i] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     } else {
         colsB[i] = make_double4(kFar, kFar, kFar, 0.0);
+        cols_d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cols_d2[i] = 0.f;
     }
 }
 
@@ -350,7 +373,13 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
                      double *gcmp, cudaStream_t st) {
     if (o.precision != UPOL_FP64 && o.precision != UPOL_MIXED) return UPOL_ERR_ARG;
     if (s->ewald && (o.precision != UPOL_FP64 || o.phase_switch)) return UPOL_ERR_ARG;
-    if (o.want_energy && !s->static_valid) {
+    // Mixed mode: ONE fp32 pass in cancellation-free difference form delivers the row potentials with the
+    // static part already removed, and the field (pair_diff.cu); no fp64 pair kernel, no static pass.
+    // The minimiser (phase_switch) launches both field kernels and lets the gate word pick one.
+    const bool mixed = o.precision == UPOL_MIXED;
+    const bool diff_energy = mixed && o.want_energy && !o.phase_switch;
+    static const bool old_mixed = getenv("UPOL_OLD_MIXED") != nullptr;      // A/B switch: round-1 field kernel
+    if (o.want_energy && !diff_energy && !s->static_valid) {
         int rc = sys_static_part(s, st);
         if (rc) return rc;
     }
@@ -358,7 +387,7 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
         prepare_shells_kernel<<<nblk(s->nb_pad, 256), 256, 0, st>>>(
             (int)s->nd, (int)s->nb_pad, s->row_site, s->r, dcmp, s->row_qs,
             s->centre[0], s->centre[1], s->centre[2], s->inv_grid, s->mix_slot, s->rowx, s->rowy, s->rowz,
-            s->cols + s->na_pad, s->cols_f);
+            s->cols + s->na_pad, s->cols_f, s->cols_d, s->cols_d2);
     }
     PairArgs a = base_args(s);
     a.rx = s->rowx; a.ry = s->rowy; a.rz = s->rowz;
@@ -368,15 +397,10 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
     UPOL_CUDA(cudaMemsetAsync(e, 0, UPOL_E_SIZE * sizeof(double), st));
     if (a.n_rows > 0) {
         const int split64 = choose_split(s, a.n_rows, a.n_tiles, fp64_rows_per_block());
-        const int splitmx = choose_split(s, a.n_rows, a.n_tiles, kBlock * kRowsMixed);
         int split_pot = 0, split_f64 = 0, split_mx = 0;
-        // The potential always needs the fp64 kernel, and that kernel delivers the field in the same pass
-        // for 1.5x the time of the potential alone - cheaper than adding a separate fp32 field pass.  So a
-        // mixed-precision call that also asks for the energy gets the fp64 field; the fp32 field kernel
-        // serves field-only calls (what a minimiser iteration is).
-        const bool mixed_field_only = o.precision == UPOL_MIXED && (!o.want_energy || o.phase_switch);
-        const bool f64_field = o.want_grad && (!mixed_field_only || o.phase_switch);
-        const bool mx_field = o.want_grad && mixed_field_only;
+        const bool f64_field = o.want_grad && (!mixed || o.phase_switch);
+        const bool f64_launch = f64_field || (o.want_energy && !diff_energy);
+        const bool mx_launch = mixed && (o.want_grad || diff_energy);
         int rc = UPOL_OK;
         if (s->ewald) {
             // periodic box: potential and field partials from the Ewald kernels, same slots
@@ -387,9 +411,7 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
             if (rc) return rc;
             if (o.want_energy) split_pot = slots;
             split_f64 = slots;
-        } else if (f64_field || o.want_energy) {
-            // fp64 kernel: potential and/or field.  With a mixed field the fp64 launch carries the
-            // potential only (energies are always fp64), unless the minimiser switches phases.
+        } else if (f64_launch) {
             PairArgs b = a;
             b.cols = s->cols;
             b.n_split = split64;
@@ -402,34 +424,44 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
             if (o.want_energy) split_pot = split64;
             if (f64_field) split_f64 = split64;
         }
-        if (mx_field && !s->ewald) {
+        if (mx_launch && !s->ewald) {
             PairArgs b = a;
-            b.cols = s->cols_f;                       // one section: core and shell of a site adjacent
-            b.n_tiles = b.n_tiles_a = (int)(s->nm_pad / kTileCols);
-            b.exA_lo = s->exM_lo; b.exA_len = s->exM_len;
-            b.n_split = splitmx;
+            const bool use_old = old_mixed && !diff_energy;
+            if (use_old) {
+                b.cols = s->cols_f;                       // one section: core and shell of a site adjacent
+                b.n_tiles = b.n_tiles_a = (int)(s->nm_pad / kTileCols);
+                b.exA_lo = s->exM_lo; b.exA_len = s->exM_len;
+                b.n_split = choose_split(s, a.n_rows, b.n_tiles, kBlock * kRowsMixed);
+            } else {
+                b.cols = s->cols_x; b.cols_d = s->cols_d; b.cols_d2 = s->cols_d2; b.dcomp = dcmp;
+                b.n_tiles_a = (int)(s->nb_pad / kTileCols);
+                b.n_tiles = (int)((s->nb_pad + s->nn_pad) / kTileCols);
+                b.exA_lo = s->exP_lo; b.exA_len = s->exP_len; b.exB_lo = s->exN_lo; b.exB_len = s->exN_len;
+                b.n_split = choose_split(s, a.n_rows, b.n_tiles, diff_rows_per_block());
+            }
             b.gate_skip_mask = kGateDone | (o.phase_switch ? kGatePhase64 : 0);
-            const bool timed = s->timing && !(f64_field || o.want_energy) && s->tev_used + 2 <= (int)s->tev.size();
+            const bool timed = s->timing && !f64_launch && s->tev_used + 2 <= (int)s->tev.size();
             if (timed) cudaEventRecord(s->tev[s->tev_used], st);
-            rc = launch_pair_mixed(b, st);
+            rc = use_old ? launch_pair_mixed(b, st) : launch_pair_diff(b, diff_energy, st);
             if (timed) { cudaEventRecord(s->tev[s->tev_used + 1], st); s->tev_used += 2; }
             if (rc) return rc;
-            split_mx = splitmx;
-            if (!o.phase_switch) split_f64 = splitmx;   // no gate: the mixed partials are THE field
+            split_mx = b.n_split;
+            if (!o.phase_switch) split_f64 = b.n_split;   // no gate: the mixed partials are THE field
+            if (diff_energy) split_pot = b.n_split;
         }
         const int nb = (int)nblk(a.n_rows, kFinRows);
         finalize_rows_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, split_pot, split_f64, split_mx,
                                                        o.gate, o.phase_switch ? 1 : 0, s->part, a.part_stride,
                                                        s->row_site, s->r, dcmp, s->row_qs, s->row_k,
                                                        s->th_ptr, s->th_row, s->th_u,
-                                                       o.want_energy ? s->phi_static : nullptr, o.want_grad, gcmp, s->eblock);
+                                                       (o.want_energy && !diff_energy) ? s->phi_static : nullptr, o.want_grad, gcmp, s->eblock);
         // eblock comps (inter, intra, self, g2) -> energy[INTER..GNORM2], contiguous by design
         reduce_blocks_kernel<<<1, 256, 0, st>>>(nb, 4, s->eblock, e + UPOL_E_INTER, 1);
         UPOL_CUDA(cudaGetLastError());
     }
     // static partial of this rank's rows, then (sharded runs) one all-reduce of the vector
     const bool reduce = o.reduce_ranks && s->nranks > 1;
-    assemble_energy_kernel<<<1, 32, 0, st>>>(e, s->e_static, o.want_energy, !reduce);
+    assemble_energy_kernel<<<1, 32, 0, st>>>(e, s->e_static, o.want_energy && !diff_energy, !reduce);
     if (reduce) {
         int rc = comm_allreduce_sum(s, e, UPOL_E_SIZE, st);
         if (rc) return rc;
@@ -533,6 +565,9 @@ int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream
     build_core_columns_kernel<<<nblk(std::max(s->na_pad, s->nm_pad), 256), 256, 0, st>>>(
         (int)s->nsite, (int)s->na_pad, s->r, s->qc, s->qs, s->centre[0], s->centre[1], s->centre[2], s->inv_grid,
         s->mix_slot, (int)(s->nsite + s->nd), (int)s->nm_pad, s->cols, s->cols_f, s->cols_static);
+    build_diff_columns_kernel<<<nblk(std::max<int64_t>(s->nsite, std::max(s->nb_pad, s->nn_pad)), 256), 256, 0, st>>>(
+        (int)s->nsite, (int)s->nd, (int)s->nb_pad, (int)s->nn_pad, s->r, s->qc, s->site_row, s->site_nslot,
+        s->centre[0], s->centre[1], s->centre[2], s->inv_grid, s->cols_x);
     if (s->nd > 0)
         build_static_rows_kernel<<<nblk(s->nd, 256), 256, 0, st>>>((int)s->nd, s->row_site, s->r,
                                                                     s->srowx, s->srowy, s->srowz);
@@ -729,7 +764,7 @@ int sys_core_forces(upol_system *s, const double *dcmp, double *dudr, cudaStream
     double *F = s->cf_tmp, *H = F + 3 * nd, *GH = H + 3 * nd;
     prepare_shells_kernel<<<nblk(s->nb_pad, 256), 256, 0, st>>>(
         (int)nd, (int)s->nb_pad, s->row_site, s->r, dcmp, s->row_qs, s->centre[0], s->centre[1], s->centre[2],
-        s->inv_grid, s->mix_slot, s->rowx, s->rowy, s->rowz, s->cols + s->na_pad, s->cols_f);
+        s->inv_grid, s->mix_slot, s->rowx, s->rowy, s->rowz, s->cols + s->na_pad, s->cols_f, s->cols_d, s->cols_d2);
     build_force_tables_kernel<<<nblk(std::max<int64_t>(n, s->nb_pad), 256), 256, 0, st>>>(
         (int)n, (int)nd, (int)s->nb_pad, s->r, s->row_site, s->row_qs, s->site_x, s->site_y, s->site_z, s->cols_dcore);
     if (s->ewald) {
