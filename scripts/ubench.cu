@@ -16,8 +16,6 @@ typedef unsigned long long u64;
 #define MUL1(d, a, b) asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b))
 #define DFMA(d, a, b, c) asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c))
 #define RSQ(d, a) asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(a))
-#define I2F(d, a) asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(d) : "r"(a))
-#define ISUB(d, a, b) asm volatile("sub.s32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b))
 
 __device__ __forceinline__ u64 pk(float lo, float hi) {
     u64 r;
@@ -31,18 +29,17 @@ __global__ void __launch_bounds__(256) k(const float *in, float *out, int iters)
     u64 x[8], y[8], a[8];
     float xf[16], yf[16], af[16];
     double xd[8], yd[8], ad[8];
-    int xi[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        x[i] = pk(in[t + i], in[t + i + 8]); y[i] = pk(in[t + 2 * i], in[t + 2 * i + 1]); a[i] = pk(in[t + 3 * i], in[t + 3 * i + 2]);
-        xd[i] = in[t + i]; yd[i] = in[t + 2 * i]; ad[i] = in[t + 3 * i];
-        xi[i] = __float_as_int(in[t + i]);
+        // disjoint index ranges: no two operands may be provably equal (the compiler would merge them)
+        x[i] = pk(in[t + i], in[t + i + 16]); y[i] = pk(in[300 + t + i], in[320 + t + i]); a[i] = pk(in[600 + t + i], in[620 + t + i]);
+        xd[i] = in[1800 + t + i]; yd[i] = in[2100 + t + i]; ad[i] = in[2400 + t + i];
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { xf[i] = in[t + i]; yf[i] = in[t + 2 * i]; af[i] = in[t + 3 * i]; }
-    const u64 A = pk(in[0], in[0]), B = pk(in[1], in[1]);
-    const float As = in[0], Bs = in[1];
-    const double Ad = in[0], Bd = in[1];
+    for (int i = 0; i < 16; ++i) { xf[i] = in[900 + t + i]; yf[i] = in[1200 + t + i]; af[i] = in[1500 + t + i]; }
+    const u64 A = pk(in[3000], in[3001]), B = pk(in[3002], in[3003]);
+    const float As = in[3004], Bs = in[3005];
+    const double Ad = in[3006], Bd = in[3007];
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -57,12 +54,10 @@ __global__ void __launch_bounds__(256) k(const float *in, float *out, int iters)
                 if (MODE == 6) DFMA(ad[i], xd[i], yd[i], ad[i]);
                 if (MODE == 7) DFMA(ad[i], ad[i], Ad, Bd);
                 if (MODE == 8) RSQ(af[i], af[i]);
-                if (MODE == 9) { int d; ISUB(d, xi[i], it); I2F(af[i], d); }   // the fixed-point difference + convert
                 if (MODE == 10) FMA2(a[i], x[i], a[i], a[i]);             // two distinct 64-bit operands (one used twice)
                 if (MODE == 11) FMA2(a[i], x[i], A, a[i]);                // one loop-invariant operand
                 if (MODE == 12) { MUL1(af[2 * i], af[2 * i], yf[2 * i]); MUL1(af[2 * i + 1], af[2 * i + 1], yf[2 * i + 1]); }
                 if (MODE == 13) { FMA2(a[i], x[i], y[i], a[i]); RSQ(af[i], af[i]); }          // FFMA2 + MUFU co-issue
-                if (MODE == 14) { FMA2(a[i], x[i], y[i], a[i]); int d; ISUB(d, xi[i], it); I2F(af[i], d); }
                 if (MODE == 15) { FMA2(a[i], x[i], y[i], a[i]); DFMA(ad[i], xd[i], yd[i], ad[i]); }   // FFMA2 + DFMA co-issue
                 if (MODE == 16) { FMA2(a[i], a[i], A, B); DFMA(ad[i], ad[i], Ad, Bd); }
                 if (MODE == 17) { FMA1(af[2 * i], xf[2 * i], yf[2 * i], af[2 * i]); FMA1(af[2 * i + 1], xf[2 * i + 1], yf[2 * i + 1], af[2 * i + 1]); DFMA(ad[i], xd[i], yd[i], ad[i]); }
@@ -123,9 +118,7 @@ int main(int argc, char **argv) {
     run<6>("DFMA   a = x*y+a         (3 distinct)", 1, in, out, mhz);
     run<7>("DFMA   a = a*A+B         (chain)", 1, in, out, mhz);
     run<8>("MUFU.RSQ", 1, in, out, mhz);
-    run<9>("IADD + I2FP              (per pair of instructions)", 1, in, out, mhz);
     run<13>("FFMA2 (3 distinct) + MUFU.RSQ     (per pair)", 1, in, out, mhz);
-    run<14>("FFMA2 (3 distinct) + IADD + I2FP  (per triple)", 1, in, out, mhz);
     run<15>("FFMA2 (3 distinct) + DFMA (3 distinct) (per pair)", 1, in, out, mhz);
     run<16>("FFMA2 chain + DFMA chain          (per pair)", 1, in, out, mhz);
     run<17>("2 FFMA (3 distinct) + DFMA (3 distinct) (per triple)", 1, in, out, mhz);

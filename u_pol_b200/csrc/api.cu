@@ -44,7 +44,7 @@ void free_system(upol_system *s) {
                     s->cols, s->cols_f, s->mix_slot, s->exM_lo, s->exM_len, s->cols_static, s->th_ptr, s->th_row, s->th_u, s->part, s->dc,
                     s->gc, s->eblock, s->energy, s->e_static, s->phi_static, s->site_row,
                     s->cols_dcore, s->site_x, s->exS_lo, s->cf_tmp,
-                    s->cols_x, s->cols_d, s->cols_d2, s->site_nslot, s->exP_lo, s->exP_len, s->exN_lo, s->exN_len};
+                    s->cols_x, s->cols_d, s->cols_d2, s->col_qeff, s->site_nslot, s->exP_lo, s->exP_len, s->exN_lo, s->exN_len};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (s->pin) cudaFreeHost(s->pin);
     if (s->hscratch) cudaFree(s->hscratch);
@@ -219,7 +219,7 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
     TRY(dev_alloc(&s->cols, s->na_pad + s->nb_pad));
     TRY(dev_alloc(&s->cols_f, s->nm_pad));
     TRY(dev_alloc(&s->mix_slot, nsite)); TRY(dev_alloc(&s->exM_lo, s->nd_pad)); TRY(dev_alloc(&s->exM_len, s->nd_pad));
-    TRY(dev_alloc(&s->cols_static, s->na_pad));
+    TRY(dev_alloc(&s->cols_static, s->na_pad)); TRY(dev_alloc(&s->col_qeff, s->na_pad));
     TRY(dev_alloc(&s->cols_x, s->nb_pad + s->nn_pad)); TRY(dev_alloc(&s->cols_d, s->nb_pad)); TRY(dev_alloc(&s->cols_d2, s->nb_pad));
     TRY(dev_alloc(&s->site_nslot, nsite));
     TRY(dev_alloc(&s->exP_lo, s->nd_pad)); TRY(dev_alloc(&s->exP_len, s->nd_pad));
@@ -229,7 +229,7 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
     s->part_elems = part_elems;
     TRY(dev_alloc(&s->dc, 3 * s->nd)); TRY(dev_alloc(&s->gc, 3 * s->nd));
     s->n_eblock = (int)((std::max<int64_t>(s->nd, nsite) + 31) / 32) + 1;   // finalize blocks hold 32 rows
-    TRY(dev_alloc(&s->eblock, 4 * (size_t)s->n_eblock));
+    TRY(dev_alloc(&s->eblock, 5 * (size_t)s->n_eblock));   // kEblockComps per finalize block
     TRY(dev_alloc(&s->energy, UPOL_E_SIZE)); TRY(dev_alloc(&s->e_static, 2)); TRY(dev_alloc(&s->phi_static, s->nd_pad));
 
     {

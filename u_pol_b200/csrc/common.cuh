@@ -63,6 +63,8 @@ struct PairArgs {
     const double *dcomp;
     const void *cols_d;
     const float *cols_d2;
+    // fused static pass of the fp64 kernel: qc_j + qs_j/2 per core column [na_pad]
+    const double *col_qeff;
     // device-side gate (minimiser): the kernel returns at once when (*gate & gate_skip_mask) != 0
     const int *gate;
     int gate_skip_mask;
@@ -73,11 +75,10 @@ constexpr int kRowsMixed = 4;
 constexpr int kGateDone = 1, kGatePhase64 = 2, kGatePhaseMixed = 4;
 constexpr int kMaxPack = 17 * 8;   // (max history + 1) x values per slot of the minimiser's scalar pack
 
-int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, cudaStream_t st);
+int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, bool fuse_static, cudaStream_t st);
 int launch_pair_mixed(const PairArgs &a, cudaStream_t st);
 int launch_pair_diff(const PairArgs &a, bool with_pot, cudaStream_t st);
-int diff_rows_per_block();
-int launch_pair_static(const PairArgs &a, cudaStream_t st);
+int diff_rows_per_block(bool with_pot);
 int launch_pair_fp64_two_fields(const PairArgs &a, cudaStream_t st);
 int fp64_rows_per_block();
 
@@ -122,7 +123,8 @@ struct upol_system {
     int *site_nslot = nullptr;    // [nsite] slot of a non-polarisable site in section N, -1 otherwise
     int *exP_lo = nullptr, *exP_len = nullptr, *exN_lo = nullptr, *exN_len = nullptr;   // [nd_pad]
     int64_t nn_pad = 0;
-    double4 *cols_static = nullptr;  // [na_pad] cores, CENTRED coordinates, q = qc + qs/2 (static pass)
+    double4 *cols_static = nullptr;  // [na_pad] cores, q = qc + qs/2 (static columns of the core-force pass and of the Ewald static pass)
+    double *col_qeff = nullptr;      // [na_pad] qc + qs/2 alone (fused static pass of the fp64 pair kernel)
     double centre[3] = {0, 0, 0};
     double inv_grid = 1.0;        // fixed-point grid: 1/grid, grid = 2^-k nm so the box fits +-2^30
     // Thole screened pairs as CSR over Drude rows (ordered pairs)

@@ -39,8 +39,6 @@
 //
 // FMA-pipe instructions per (row, polarisable site): 45 with the energy, 26 field only; per (row,
 // other site) 23 / 12; MUFU 5 / 2 and 3 / 1.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "f32x2.cuh"
 
@@ -106,21 +104,8 @@ __device__ __forceinline__ void diff_site_careful(const int4 c, const float4 cd,
 
 }  // namespace
 
-// OPT bit 0: FMAs with three distinct 64-bit register operands are issued as two scalar FFMAs (measured:
-// FFMA2 with three distinct register pairs costs 4.0 cycles per warp and SM sub-partition, two scalar
-// FFMAs 3.2; the register file delivers two 32-bit operands per lane and cycle - scripts/ubench.cu).
-// OPT bit 1: the same for FFMA2 with one broadcast (32-bit) and two 64-bit operands.
-template <bool SCALAR>
-__device__ __forceinline__ f32x2 fmaX(f32x2 a, f32x2 b, f32x2 c) {
-    if (!SCALAR) return fma2(a, b, c);
-    float a0, a1, b0, b1, c0, c1;
-    unpack2(a, a0, a1); unpack2(b, b0, b1); unpack2(c, c0, c1);
-    return pack2(fmaf(a0, b0, c0), fmaf(a1, b1, c1));
-}
-
-template <int ROWS, bool POT, int MINB, int OPT>
+template <int ROWS, bool POT, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs a) {
-    constexpr bool S3 = (OPT & 1) != 0, S5 = (OPT & 2) != 0;
     static_assert(ROWS % 2 == 0, "rows are processed in fp32 pairs");
     constexpr int NP = ROWS / 2;
     __shared__ int4 shX[kTileCols];
@@ -218,29 +203,29 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
                         const f32x2 A2 = fma2(Az, Az, fma2(Ay, Ay, mul2(Ax, Ax)));
                         const f32x2 yA = rsqrt2(A2);
                         const f32x2 pa = mul2(qc2, yA);
-                        const f32x2 DCA = fmaX<S5>(Ax, mx2, fmaX<S5>(Ay, my2, fma2(Az, mz2, dj2)));   // |C|^2 - |A|^2
+                        const f32x2 DCA = fma2(Ax, mx2, fma2(Ay, my2, fma2(Az, mz2, dj2)));   // |C|^2 - |A|^2
                         const f32x2 C2 = add2(A2, DCA);
                         const f32x2 yC = rsqrt2(C2);
                         const f32x2 pc = mul2(qs2, yC);
                         if (POT) {
-                            const f32x2 DA = fmaX<S3>(Ax, T2x[p], fmaX<S3>(Ay, T2y[p], fmaX<S3>(Az, T2z[p], ND2[p])));  // |A|^2 - |R|^2
+                            const f32x2 DA = fma2(Ax, T2x[p], fma2(Ay, T2y[p], fma2(Az, T2z[p], ND2[p])));  // |A|^2 - |R|^2
                             const f32x2 R2 = sub2(A2, DA);
                             const f32x2 DC = add2(DA, DCA);                                         // |C|^2 - |R|^2
                             const f32x2 yR = rsqrt2(R2);
                             const f32x2 nR = mul2(R2, yR);
-                            const f32x2 uA = mul2(yR, rcp2(fmaX<S3>(A2, yA, nR)));
-                            const f32x2 uC = mul2(yR, rcp2(fmaX<S3>(C2, yC, nR)));
-                            PA[p] = fmaX<S3>(pa, mul2(DA, uA), PA[p]);    // -qc [f(A) - f(R)]
-                            PC[p] = fmaX<S3>(pc, mul2(DC, uC), PC[p]);    // -qs [f(C) - f(R)]
+                            const f32x2 uA = mul2(yR, rcp2(fma2(A2, yA, nR)));
+                            const f32x2 uC = mul2(yR, rcp2(fma2(C2, yC, nR)));
+                            PA[p] = fma2(pa, mul2(DA, uA), PA[p]);    // -qc [f(A) - f(R)]
+                            PC[p] = fma2(pc, mul2(DC, uC), PC[p]);    // -qs [f(C) - f(R)]
                         }
                         const f32x2 yA2 = mul2(yA, yA), yC2 = mul2(yC, yC);
                         const f32x2 meA = fma2(A2, yA2, mone2), meC = fma2(C2, yC2, mone2);      // -(1 - |X|^2 y^2)
                         const f32x2 zA = mul2(pa, yA2), zC = mul2(pc, yC2);
                         // w_A + w_C with both seed corrections in one go; the -w_C d_j part is |d_j|/|A| times
                         // smaller than the gross terms and takes the uncorrected z_C
-                        const f32x2 wS = fma2(fmaX<S3>(zC, meC, mul2(zA, meA)), m15, add2(zA, zC));
-                        Fx[p] = fmaX<S3>(wS, Ax, Fx[p]); Fy[p] = fmaX<S3>(wS, Ay, Fy[p]); Fz[p] = fmaX<S3>(wS, Az, Fz[p]);
-                        Hx[p] = fmaX<S5>(zC, mx2, Hx[p]); Hy[p] = fmaX<S5>(zC, my2, Hy[p]); Hz[p] = fmaX<S5>(zC, mz2, Hz[p]);
+                        const f32x2 wS = fma2(fma2(zC, meC, mul2(zA, meA)), m15, add2(zA, zC));
+                        Fx[p] = fma2(wS, Ax, Fx[p]); Fy[p] = fma2(wS, Ay, Fy[p]); Fz[p] = fma2(wS, Az, Fz[p]);
+                        Hx[p] = fma2(zC, mx2, Hx[p]); Hy[p] = fma2(zC, my2, Hy[p]); Hz[p] = fma2(zC, mz2, Hz[p]);
                     }
                 }
             } else {
@@ -257,17 +242,17 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
                         const f32x2 yA = rsqrt2(A2);
                         const f32x2 pa = mul2(qc2, yA);
                         if (POT) {
-                            const f32x2 DA = fmaX<S3>(Ax, T2x[p], fmaX<S3>(Ay, T2y[p], fmaX<S3>(Az, T2z[p], ND2[p])));
+                            const f32x2 DA = fma2(Ax, T2x[p], fma2(Ay, T2y[p], fma2(Az, T2z[p], ND2[p])));
                             const f32x2 R2 = sub2(A2, DA);
                             const f32x2 yR = rsqrt2(R2);
-                            const f32x2 uA = mul2(yR, rcp2(fmaX<S3>(A2, yA, mul2(R2, yR))));
-                            PA[p] = fmaX<S3>(pa, mul2(DA, uA), PA[p]);
+                            const f32x2 uA = mul2(yR, rcp2(fma2(A2, yA, mul2(R2, yR))));
+                            PA[p] = fma2(pa, mul2(DA, uA), PA[p]);
                         }
                         const f32x2 yA2 = mul2(yA, yA);
                         const f32x2 meA = fma2(A2, yA2, mone2);
                         const f32x2 zA = mul2(pa, yA2);
                         const f32x2 wA = fma2(mul2(zA, meA), m15, zA);
-                        Fx[p] = fmaX<S3>(wA, Ax, Fx[p]); Fy[p] = fmaX<S3>(wA, Ay, Fy[p]); Fz[p] = fmaX<S3>(wA, Az, Fz[p]);
+                        Fx[p] = fma2(wA, Ax, Fx[p]); Fy[p] = fma2(wA, Ay, Fy[p]); Fz[p] = fma2(wA, Az, Fz[p]);
                     }
                 }
             }
@@ -335,40 +320,23 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
     }
 }
 
-// Variant table (rows per thread, min resident blocks): measured on the 100 k-Drude box, see
-// profiles/r02_diff_variants.txt; UPOL_DIFF_VARIANT overrides the default for such sweeps.
-static int diff_variant() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("UPOL_DIFF_VARIANT"); v = e ? atoi(e) : 0; }
-    return v;
-}
+// Launch shapes measured on the 100 k-Drude box (profiles/r02_diff_variants.txt): with the energy,
+// 2 rows per thread and 4 resident blocks (128 registers) 22.8 ms against 24.8 ms for 4 rows (246
+// registers, 2 blocks); field only, 4 rows (164 registers, 3 blocks) 14.3 ms against 14.7 ms.  Issuing the
+// FMAs that have three distinct register-pair operands as two scalar FFMAs each was measured slower
+// (25.0 ms / 15.0 ms) although such an FFMA2 costs 4.0 cycles and two FFMAs 3.2 in isolation
+// (scripts/ubench.cu, profiles/r02_ubench.txt): the loop is bound by register-file operand reads, and
+// the scalar form adds issue slots without removing any.
+constexpr int kDiffRowsPot = 2, kDiffRowsField = 4;
 
-int diff_rows_per_block() { const int v = diff_variant() % 4; return kBlock * (v >= 2 ? 2 : 4); }
-
-template <int ROWS, int MINB, int OPT>
-static void launch_diff_variant(const PairArgs &a, bool with_pot, cudaStream_t st) {
-    dim3 grid((unsigned)((a.n_rows + kBlock * ROWS - 1) / (kBlock * ROWS)), (unsigned)a.n_split);
-    if (with_pot) pair_diff_kernel<ROWS, true, MINB, OPT><<<grid, kBlock, 0, st>>>(a);
-    else pair_diff_kernel<ROWS, false, MINB, OPT><<<grid, kBlock, 0, st>>>(a);
-}
-
-template <int OPT>
-static void launch_diff_opt(const PairArgs &a, bool with_pot, cudaStream_t st) {
-    switch (diff_variant() % 4) {
-        case 1: launch_diff_variant<4, 3, OPT>(a, with_pot, st); break;
-        case 2: launch_diff_variant<2, 1, OPT>(a, with_pot, st); break;
-        case 3: launch_diff_variant<2, 4, OPT>(a, with_pot, st); break;
-        default: launch_diff_variant<4, 1, OPT>(a, with_pot, st); break;
-    }
-}
+int diff_rows_per_block(bool with_pot) { return kBlock * (with_pot ? kDiffRowsPot : kDiffRowsField); }
 
 int launch_pair_diff(const PairArgs &a, bool with_pot, cudaStream_t st) {
     if (a.n_rows <= 0) return UPOL_OK;
-    switch (diff_variant() / 4) {
-        case 1: launch_diff_opt<1>(a, with_pot, st); break;
-        case 2: launch_diff_opt<3>(a, with_pot, st); break;
-        default: launch_diff_opt<0>(a, with_pot, st); break;
-    }
+    const int rpb = diff_rows_per_block(with_pot);
+    dim3 grid((unsigned)((a.n_rows + rpb - 1) / rpb), (unsigned)a.n_split);
+    if (with_pot) pair_diff_kernel<kDiffRowsPot, true, 4><<<grid, kBlock, 0, st>>>(a);
+    else pair_diff_kernel<kDiffRowsField, false, 1><<<grid, kBlock, 0, st>>>(a);
     UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
 }

@@ -14,8 +14,8 @@
 // Kernels in this file
 //   pair_fp64_kernel<ROWS, POT, GRAD, MINB, SPLITF>  fp64 potential and/or field (K1); SPLITF keeps the
 //                                                     fields of the two column sections apart (core forces)
-//   pair_static_kernel<ROWS>                          fp64 static potential at the Drude cores (K3),
-//                                                     expanded squared distance, 10 DP ops per interaction
+//                                                     FUSE adds the static potential at the Drude cores (K3)
+//                                                     from the same core tiles, 10 DP ops per interaction
 //   pair_mixed_kernel<ROWS>                           field only: fixed-point coordinates, fp32 pair math,
 //                                                     fp64 accumulation
 //
@@ -76,9 +76,17 @@ __device__ __forceinline__ double rsqrt_f64(double x) {
 
 // SPLITF (core-force pass): the fields of section A and section B are kept apart, because they are
 // multiplied by different charges of the row afterwards (output comps 0-2 and 3-5, no potential).
-template <int ROWS, bool POT, bool GRAD, int MINB, bool SPLITF = false>
+//
+// FUSE (with POT): the d-independent static potential  phi_static_i = sum_j (qc_j + qs_j/2) / |r_j - r_i|
+// (polarization.py:50-61, :82) is formed in the same pass from the core tiles: R = r_j - r_i = A - d_i, so
+// |R|^2 = |A|^2 - 2 A.d_i + |d_i|^2 costs one add and three FMAs on top of the A already in registers.  One
+// launch and one column sweep instead of two; the partial goes to slot 5 and finalize_rows_kernel
+// subtracts it row by row (and keeps it, so later evaluations of the same geometry skip it).
+template <int ROWS, bool POT, bool GRAD, int MINB, bool SPLITF = false, bool FUSE = false>
 __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs a) {
+    static_assert(!FUSE || POT, "the static potential rides on the potential pass");
     __shared__ double4 sh[kTileCols];
+    __shared__ double shq[FUSE ? kTileCols : 1];
     if (a.gate != nullptr && (*a.gate & a.gate_skip_mask) != 0) return;   // minimiser: converged / other phase
     const double4 *__restrict__ cols = static_cast<const double4 *>(a.cols);
 
@@ -87,6 +95,8 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
     double sx[ROWS], sy[ROWS], sz[ROWS];
     int loA[ROWS], lenA[ROWS], loB[ROWS], lenB[ROWS];
     double phA[ROWS], phB[ROWS], plA[ROWS], plB[ROWS], fx[ROWS], fy[ROWS], fz[ROWS];
+    double m2x[FUSE ? ROWS : 1], m2y[FUSE ? ROWS : 1], m2z[FUSE ? ROWS : 1], dd[FUSE ? ROWS : 1];   // -2 d_i, |d_i|^2
+    double psH[FUSE ? ROWS : 1], psL[FUSE ? ROWS : 1];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         const int lr = row_base + r * kBlock;
@@ -96,6 +106,13 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
         loA[r] = a.exA_lo[i]; lenA[r] = a.exA_len[i];
         loB[r] = a.exB_lo[i]; lenB[r] = a.exB_len[i];
         phA[r] = phB[r] = plA[r] = plB[r] = fx[r] = fy[r] = fz[r] = 0.0;
+        if (FUSE) {
+            constexpr int q = FUSE ? 1 : 0;
+            const double dx = a.dcomp[3 * i], dy = a.dcomp[3 * i + 1], dz = a.dcomp[3 * i + 2];
+            m2x[q * r] = -2.0 * dx; m2y[q * r] = -2.0 * dy; m2z[q * r] = -2.0 * dz;
+            dd[q * r] = fma(dz, dz, fma(dy, dy, dx * dx));
+            psH[q * r] = psL[q * r] = 0.0;
+        }
     }
 
     const int t0 = (int)(((int64_t)a.n_tiles * blockIdx.y) / a.n_split);
@@ -112,8 +129,12 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
         const bool isB = t >= a.n_tiles_a;
         const double4 *src = (cols_b != nullptr && isB) ? cols_b + (int64_t)(t - a.n_tiles_a) * kTileCols : cols + base;
         __syncthreads();
-        for (int j = tid; j < kTileCols; j += kBlock) sh[j] = src[j];
+        for (int j = tid; j < kTileCols; j += kBlock) {
+            sh[j] = src[j];
+            if (FUSE && !isB) shq[j] = a.col_qeff[base + j];
+        }
         __syncthreads();
+        const bool stat = FUSE && !isB;            // this tile also feeds the static potential
         if (SPLITF && t == a.n_tiles_a) {
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) { gx[r] = fx[r]; gy[r] = fy[r]; gz[r] = fz[r]; fx[r] = fy[r] = fz[r] = 0.0; }
@@ -128,12 +149,40 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
             need |= (lo[r] < kTileCols) && (lo[r] + len[r] > 0);
         }
         // tile-local sums: the compare-free loop below is speculative and may have to be redone
-        double ph[ROWS], tx[ROWS], ty[ROWS], tz[ROWS];
+        double ph[ROWS], tx[ROWS], ty[ROWS], tz[ROWS], pst[FUSE ? ROWS : 1];
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) ph[r] = tx[r] = ty[r] = tz[r] = 0.0;
+        for (int r = 0; r < ROWS; ++r) { ph[r] = tx[r] = ty[r] = tz[r] = 0.0; if (FUSE) pst[FUSE ? r : 0] = 0.0; }
 
         bool careful = __any_sync(0xffffffffu, need);
-        if (!careful) {
+        if (!careful && stat) {
+            // core tile of the fused pass: the loop below plus |R|^2 from A and one more reciprocal root
+            int hmin = 0x7fffffff;
+#pragma unroll 2
+            for (int j = 0; j < kTileCols; ++j) {
+                const double4 c = sh[j];
+                const double qe = shq[j];
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const double dx = c.x - sx[r], dy = c.y - sy[r], dz = c.z - sz[r];
+                    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    const double R2 = fma(dx, m2x[FUSE ? r : 0], fma(dy, m2y[FUSE ? r : 0], fma(dz, m2z[FUSE ? r : 0], r2 + dd[FUSE ? r : 0])));
+                    hmin = min(hmin, min(__double2hiint(r2), __double2hiint(R2)));
+                    pst[FUSE ? r : 0] = fma(qe, rsqrt_f64(R2), pst[FUSE ? r : 0]);
+                    const double inv = rsqrt_f64(r2);
+                    const double tq = c.w * inv;
+                    ph[r] += tq;
+                    if (GRAD) {
+                        const double w = tq * (inv * inv);
+                        tx[r] = fma(w, dx, tx[r]); ty[r] = fma(w, dy, ty[r]); tz[r] = fma(w, dz, tz[r]);
+                    }
+                }
+            }
+            careful = __any_sync(0xffffffffu, hmin < kZeroR2Hi);
+            if (careful) {
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) { ph[r] = tx[r] = ty[r] = tz[r] = 0.0; pst[FUSE ? r : 0] = 0.0; }
+            }
+        } else if (!careful) {
             // no same-molecule column in this tile for any row of the warp.  No per-pair selects either:
             // only an integer min of the high word of r^2 (ALU pipe); a zero-distance pair
             // (polarization.py:33-42: term dropped) is caught after the tile, which is then redone
@@ -176,7 +225,15 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
                 for (int r = 0; r < ROWS; ++r) {
                     const double dx = c.x - sx[r], dy = c.y - sy[r], dz = c.z - sz[r];
                     double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    const bool drop = ((unsigned)(j - lo[r]) < (unsigned)len[r]) || (__double2hiint(r2) < kZeroR2Hi);
+                    const bool excl = (unsigned)(j - lo[r]) < (unsigned)len[r];
+                    if (FUSE && stat) {
+                        // f(R) is dropped on its own when ITS distance vanishes (polarization.py:33-42)
+                        double R2 = fma(dx, m2x[FUSE ? r : 0], fma(dy, m2y[FUSE ? r : 0], fma(dz, m2z[FUSE ? r : 0], r2 + dd[FUSE ? r : 0])));
+                        const bool dropR = excl || (__double2hiint(R2) < kZeroR2Hi);
+                        R2 = dropR ? 1.0 : R2;
+                        pst[FUSE ? r : 0] = fma(dropR ? 0.0 : shq[FUSE ? j : 0], rsqrt_f64(R2), pst[FUSE ? r : 0]);
+                    }
+                    const bool drop = excl || (__double2hiint(r2) < kZeroR2Hi);
                     const double q = drop ? 0.0 : c.w;
                     r2 = drop ? 1.0 : r2;
                     if (POT) {
@@ -202,6 +259,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 if (isB) two_sum_acc(phB[r], plB[r], ph[r]); else two_sum_acc(phA[r], plA[r], ph[r]);
+                if (FUSE && stat) two_sum_acc(psH[FUSE ? r : 0], psL[FUSE ? r : 0], pst[FUSE ? r : 0]);
             }
         }
     }
@@ -226,6 +284,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
                 out[0 * a.part_stride + lr] = phA[r] + plA[r];
                 out[1 * a.part_stride + lr] = phB[r] + plB[r];
             }
+            if (FUSE) out[5 * a.part_stride + lr] = psH[FUSE ? r : 0] + psL[FUSE ? r : 0];
             if (GRAD) {
                 out[2 * a.part_stride + lr] = fx[r];
                 out[3 * a.part_stride + lr] = fy[r];
@@ -253,106 +312,6 @@ __device__ __forceinline__ float rsqrt_f32(float x) {
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // bare MUFU.RSQ, no denormal fix-up
     return y;
-}
-
-// K3: d-independent static potential at the Drude core positions,
-//   phi_static_i = sum_{j not in mol(i)} (qc_j + qs_j/2) / |r_j - r_i|        (polarization.py:50-61, :82).
-// Potential only, so no displacement vector is needed and the squared distance is expanded,
-//   |x - r|^2 = (|x|^2 + |r|^2) - 2 x.r   (1 add + 3 FMA instead of 3 sub + 1 mul + 2 FMA),
-// on coordinates centred on the box (cancellation error ~ 2e-16 (|x|^2 + |r|^2), i.e. < 1e-12 of
-// r^2 even for contact pairs in a 14 nm box).  |x|^2 is formed once per column when the tile is
-// staged.  10 DP ops per interaction instead of 12.
-template <int ROWS>
-__global__ void __launch_bounds__(kBlock) pair_static_kernel(const PairArgs a) {
-    __shared__ double4 sh[kTileCols];
-    __shared__ double sh2[kTileCols];
-    const double4 *__restrict__ cols = static_cast<const double4 *>(a.cols);   // x, y, z, q_eff (centred at staging)
-
-    const int tid = threadIdx.x;
-    const int row_base = blockIdx.x * (kBlock * ROWS) + tid;
-    double mx[ROWS], my[ROWS], mz[ROWS], r2i[ROWS], ph[ROWS], pl[ROWS];
-    int lo[ROWS], len[ROWS];
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const int lr = row_base + r * kBlock;
-        const int i = a.row0 + (lr < a.n_rows ? lr : 0);
-        const double x = a.rx[i] - a.cx, y = a.ry[i] - a.cy, z = a.rz[i] - a.cz;
-        mx[r] = -2.0 * x; my[r] = -2.0 * y; mz[r] = -2.0 * z;
-        r2i[r] = fma(z, z, fma(y, y, x * x));
-        lo[r] = a.exA_lo[i]; len[r] = a.exA_len[i];
-        ph[r] = pl[r] = 0.0;
-    }
-    const int t0 = (int)(((int64_t)a.n_tiles * blockIdx.y) / a.n_split);
-    const int t1 = (int)(((int64_t)a.n_tiles * (blockIdx.y + 1)) / a.n_split);
-    for (int t = t0; t < t1; ++t) {
-        const int base = t * kTileCols;
-        __syncthreads();
-        for (int j = tid; j < kTileCols; j += kBlock) {
-            double4 c = cols[base + j];
-            c.x -= a.cx; c.y -= a.cy; c.z -= a.cz;
-            sh[j] = c;
-            sh2[j] = fma(c.z, c.z, fma(c.y, c.y, c.x * c.x));
-        }
-        __syncthreads();
-        bool need = false;
-        int rel[ROWS];
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            rel[r] = lo[r] - base;
-            need |= (rel[r] < kTileCols) && (rel[r] + len[r] > 0);
-        }
-        double pt[ROWS];
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) pt[r] = 0.0;
-        bool careful = __any_sync(0xffffffffu, need);
-        if (!careful) {
-            // speculative compare-free loop: no per-pair selects, only an integer min of the high word
-            // of r^2 (ALU pipe).  A zero-distance pair (r^2 below the cancellation noise) is caught
-            // after the tile and the tile is redone with the predicated loop; pt is tile-local, so
-            // nothing has to be undone.
-            int hmin = 0x7fffffff;
-#pragma unroll 4
-            for (int j = 0; j < kTileCols; ++j) {
-                const double4 c = sh[j];
-                const double x2 = sh2[j];
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    const double r2 = fma(mx[r], c.x, fma(my[r], c.y, fma(mz[r], c.z, x2 + r2i[r])));
-                    hmin = min(hmin, __double2hiint(r2));
-                    pt[r] = fma(c.w, rsqrt_f64(r2), pt[r]);
-                }
-            }
-            careful = __any_sync(0xffffffffu, hmin < kZeroR2Hi);
-            if (careful) {
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) pt[r] = 0.0;
-            }
-        }
-        if (careful) {
-#pragma unroll 2
-            for (int j = 0; j < kTileCols; ++j) {
-                const double4 c = sh[j];
-                const double x2 = sh2[j];
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    double r2 = fma(mx[r], c.x, fma(my[r], c.y, fma(mz[r], c.z, x2 + r2i[r])));
-                    // zero distance (|r| < 1e-5 nm once the cancellation noise is allowed for): dropped
-                    const bool drop = ((unsigned)(j - rel[r]) < (unsigned)len[r]) || (__double2hiint(r2) < kZeroR2Hi);
-                    const double q = drop ? 0.0 : c.w;
-                    r2 = drop ? 1.0 : r2;
-                    pt[r] = fma(q, rsqrt_f64(r2), pt[r]);
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) two_sum_acc(ph[r], pl[r], pt[r]);
-    }
-    double *out = a.part + (int64_t)blockIdx.y * kPartComps * a.part_stride;
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const int lr = row_base + r * kBlock;
-        if (lr < a.n_rows) out[lr] = ph[r] + pl[r];
-    }
 }
 
 // q / r^3 from r^2: MUFU.RSQ seed y (rel. error eps <= 2^-22.9) and a first-order correction of
@@ -507,9 +466,12 @@ __global__ void __launch_bounds__(kBlock) pair_mixed_kernel(const PairArgs a) {
 }
 
 template <int ROWS, int MINB>
-static void launch_fp64_variant(const PairArgs &a, bool with_pot, bool with_grad, cudaStream_t st) {
+static void launch_fp64_variant(const PairArgs &a, bool with_pot, bool with_grad, bool fuse_static, cudaStream_t st) {
     dim3 grid((unsigned)((a.n_rows + kBlock * ROWS - 1) / (kBlock * ROWS)), (unsigned)a.n_split);
-    if (with_pot && with_grad)
+    if (with_pot && fuse_static) {
+        if (with_grad) pair_fp64_kernel<ROWS, true, true, 3, false, true><<<grid, kBlock, 0, st>>>(a);   // 3 resident blocks: <= 168 registers
+        else pair_fp64_kernel<ROWS, true, false, MINB, false, true><<<grid, kBlock, 0, st>>>(a);
+    } else if (with_pot && with_grad)
         pair_fp64_kernel<ROWS, true, true, MINB><<<grid, kBlock, 0, st>>>(a);
     else if (with_grad)
         pair_fp64_kernel<ROWS, false, true, MINB><<<grid, kBlock, 0, st>>>(a);
@@ -522,9 +484,9 @@ int fp64_rows_per_block() { return kRowTile; }
 // Variants tried on the 100 k-Drude box (profiles/r01_variant_sweep.txt): 1/2/3/4 rows per thread,
 // min-blocks 1/3/4/6/8 - all within 5 %; occupancy is not the limiter (the FP64 pipe is, ~80 %
 // busy), so the plain 2-rows / no-min-blocks build stays.
-int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, cudaStream_t st) {
+int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, bool fuse_static, cudaStream_t st) {
     if (a.n_rows <= 0) return UPOL_OK;
-    launch_fp64_variant<kRowsPerThread, 1>(a, with_pot, with_grad, st);
+    launch_fp64_variant<kRowsPerThread, 1>(a, with_pot, with_grad, fuse_static, st);
     UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
 }
@@ -533,15 +495,6 @@ int launch_pair_fp64_two_fields(const PairArgs &a, cudaStream_t st) {
     if (a.n_rows <= 0) return UPOL_OK;
     dim3 grid((unsigned)((a.n_rows + kRowTile - 1) / kRowTile), (unsigned)a.n_split);
     pair_fp64_kernel<kRowsPerThread, false, true, 1, true><<<grid, kBlock, 0, st>>>(a);
-    UPOL_CUDA(cudaGetLastError());
-    return UPOL_OK;
-}
-
-int launch_pair_static(const PairArgs &a, cudaStream_t st) {
-    if (a.n_rows <= 0) return UPOL_OK;
-    // 2, 3 and 4 rows per thread measured within 2 % of each other (profiles/r01_config_table.txt)
-    dim3 grid((unsigned)((a.n_rows + kRowTile - 1) / kRowTile), (unsigned)a.n_split);
-    pair_static_kernel<kRowsPerThread><<<grid, kBlock, 0, st>>>(a);
     UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
 }

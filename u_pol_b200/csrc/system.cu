@@ -38,7 +38,7 @@ __global__ void build_core_columns_kernel(int nsite, int na_pad, const double *_
                                           double cx, double cy, double cz, double inv_grid,
                                           const int *__restrict__ mix_slot, int n_mix, int nm_pad,
                                           double4 *__restrict__ cols, int4 *__restrict__ cols_f,
-                                          double4 *__restrict__ cols_static) {
+                                          double4 *__restrict__ cols_static, double *__restrict__ col_qeff) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nm_pad - n_mix) cols_f[n_mix + i] = make_int4(kFixFar, kFixFar, kFixFar, 0);   // tail padding
     if (i >= na_pad) return;
@@ -47,9 +47,11 @@ __global__ void build_core_columns_kernel(int nsite, int na_pad, const double *_
         cols[i] = make_double4(x, y, z, qc[i]);
         cols_f[mix_slot[i]] = fix_col(x - cx, y - cy, z - cz, inv_grid, qc[i]);
         cols_static[i] = make_double4(x, y, z, qc[i] + 0.5 * qs[i]);
+        col_qeff[i] = qc[i] + 0.5 * qs[i];
     } else {
         cols[i] = make_double4(kFar, kFar, kFar, 0.0);
         cols_static[i] = make_double4(kFar, kFar, kFar, 0.0);
+        col_qeff[i] = 0.0;
     }
 }
 
@@ -134,6 +136,7 @@ __device__ __forceinline__ double block_sum(double v, double *sm) {
 }
 
 constexpr int kFinBlock = 128;
+constexpr int kEblockComps = 5;   // per finalize block: inter, intra, self, |g|^2, static (= energy[INTER..STATIC])
 constexpr int kFinRows = 32;      // rows per finalize block: 32 rows x 4 split lanes
 constexpr int kFinLanes = kFinBlock / kFinRows;
 
@@ -169,13 +172,13 @@ __device__ __forceinline__ void fold_splits(const double *__restrict__ part, int
 // K4b + K2: per Drude row, fold the column-split partials, apply K*qs, add the spring and the
 // intra-molecular Thole pairs, write the gradient row, and emit per-block energy partials.
 __global__ void __launch_bounds__(kFinBlock)
-finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int n_split_mixed,
+finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int n_split_mixed, int fused_static,
                      const int *__restrict__ gate, int phase_switch, const double *__restrict__ part, int64_t stride,
                      const int *__restrict__ row_site, const double *__restrict__ r,
                      const double *__restrict__ dc, const double *__restrict__ row_qs,
                      const double *__restrict__ row_k,
                      const int *__restrict__ th_ptr, const int *__restrict__ th_row,
-                     const double *__restrict__ th_u, const double *__restrict__ phi_static,
+                     const double *__restrict__ th_u, double *__restrict__ phi_static,
                      bool with_grad, double *__restrict__ gc, double *__restrict__ eblock) {
     __shared__ double sm[kFinBlock / 32];
     __shared__ double fold[kFinLanes][kFinRows][kPartComps];
@@ -186,17 +189,21 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
     const int lr = blockIdx.x * kFinRows + threadIdx.x % kFinRows;
     const bool live = lr < n_rows;
     const bool owner = live && threadIdx.x < kFinRows;
-    double pot[2] = {0.0, 0.0}, frc[3] = {0.0, 0.0, 0.0};
+    double pot[2] = {0.0, 0.0}, frc[3] = {0.0, 0.0, 0.0}, stat[1] = {0.0};
     if (n_split_pot > 0) fold_splits<2>(part, stride, lr, live, n_split_pot, 0, fold, pot);
     if (with_grad) fold_splits<3>(part, stride, lr, live, n_split_f, 2, fold, frc);
-    double e_inter = 0.0, e_intra = 0.0, e_self = 0.0, g2 = 0.0;
+    // fused pass: the static potential of the row arrives as slot 5 of the same launch; it is kept
+    // (phi_static) so that later evaluations of this geometry need not form it again
+    if (fused_static) fold_splits<1>(part, stride, lr, live, n_split_pot, 5, fold, stat);
+    double e_inter = 0.0, e_intra = 0.0, e_self = 0.0, g2 = 0.0, e_stat = 0.0;
     if (owner) {
         const int i = row0 + lr;
         const double pa = pot[0], pb = pot[1], fx = frc[0], fy = frc[1], fz = frc[2];
         const double qs = row_qs[i], kk = row_k[i];
         const double dx = dc[3 * i], dy = dc[3 * i + 1], dz = dc[3 * i + 2];
         // (U_coul - U_coul_static) share of the row: static potential removed before the row sum
-        const double ps = phi_static ? phi_static[i] : 0.0;
+        const double ps = fused_static ? stat[0] : (phi_static ? phi_static[i] : 0.0);
+        if (fused_static) { phi_static[i] = ps; e_stat = -kCoulomb * qs * ps; }
         e_inter = kCoulomb * qs * ((pa - ps) + 0.5 * pb);
         e_self = 0.5 * kk * (dx * dx + dy * dy + dz * dz);
         double gx = -kCoulomb * qs * fx + kk * dx;
@@ -233,9 +240,10 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
     const double s1 = block_sum<kFinBlock>(e_intra, sm);
     const double s2 = block_sum<kFinBlock>(e_self, sm);
     const double s3 = block_sum<kFinBlock>(g2, sm);
+    const double s4 = fused_static ? block_sum<kFinBlock>(e_stat, sm) : 0.0;
     if (threadIdx.x == 0) {
-        double *o = eblock + 4 * (int64_t)blockIdx.x;
-        o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
+        double *o = eblock + kEblockComps * (int64_t)blockIdx.x;
+        o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3; o[4] = s4;
     }
 }
 
@@ -277,9 +285,10 @@ __global__ void reduce_blocks_kernel(int nblock, int ncomp, const double *__rest
 }
 
 // energy vector assembly: e[INTER], e[INTRA], e[SELF], e[GNORM2] hold (all-reduced) partial sums
-__global__ void assemble_energy_kernel(double *__restrict__ e, const double *__restrict__ e_static,
-                                       bool put_static, bool total) {
+__global__ void assemble_energy_kernel(double *__restrict__ e, double *__restrict__ e_static,
+                                       bool put_static, bool total, bool save_static = false) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (save_static) e_static[0] = e[UPOL_E_STATIC];     // fused pass: this rank's partial, kept with phi_static
         if (put_static) e[UPOL_E_STATIC] = e_static[0];      // informational; already inside E_INTER
         if (total) e[UPOL_E_UIND] = (e[UPOL_E_INTER] + e[UPOL_E_INTRA]) + e[UPOL_E_SELF];
     }
@@ -355,7 +364,10 @@ int sys_static_part(upol_system *s, cudaStream_t st) {
     a.n_split = choose_split(s, a.n_rows, a.n_tiles, fp64_rows_per_block());
     if (a.n_rows > 0) {
         // periodic box: same rows and columns, Ewald pair function (ewald.cu) instead of 1/r
-        int rc = s->ewald ? ewald_static_part(s, a, &a.n_split, st) : launch_pair_static(a, st);
+        // periodic boxes only (same rows and columns, Ewald pair function, ewald.cu); under open boundaries
+        // the static potential is fused into the main fp64 pass (pair_fp64_kernel<FUSE>)
+        if (!s->ewald) return UPOL_ERR_ARG;
+        int rc = ewald_static_part(s, a, &a.n_split, st);
         if (rc) return rc;
         const int nb = (int)nblk(a.n_rows, kFinRows);
         finalize_static_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, a.n_split, s->part, a.part_stride,
@@ -379,7 +391,10 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
     const bool mixed = o.precision == UPOL_MIXED;
     const bool diff_energy = mixed && o.want_energy && !o.phase_switch;
     static const bool old_mixed = getenv("UPOL_OLD_MIXED") != nullptr;      // A/B switch: round-1 field kernel
-    if (o.want_energy && !diff_energy && !s->static_valid) {
+    // fp64 energies need the static potential of the rows: cached per geometry; formed by the Ewald kernels
+    // under a box, and inside the main pass (fused) under open boundaries
+    const bool fuse_static = o.want_energy && !diff_energy && !s->static_valid && !s->ewald;
+    if (o.want_energy && !diff_energy && !s->static_valid && s->ewald) {
         int rc = sys_static_part(s, st);
         if (rc) return rc;
     }
@@ -415,10 +430,11 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
             PairArgs b = a;
             b.cols = s->cols;
             b.n_split = split64;
+            b.dcomp = dcmp; b.col_qeff = s->col_qeff;
             b.gate_skip_mask = kGateDone | (o.phase_switch ? kGatePhaseMixed : 0);
             const bool timed = s->timing && s->tev_used + 2 <= (int)s->tev.size();
             if (timed) cudaEventRecord(s->tev[s->tev_used], st);
-            rc = launch_pair_fp64(b, o.want_energy, f64_field, st);
+            rc = launch_pair_fp64(b, o.want_energy, f64_field, fuse_static, st);
             if (timed) { cudaEventRecord(s->tev[s->tev_used + 1], st); s->tev_used += 2; }
             if (rc) return rc;
             if (o.want_energy) split_pot = split64;
@@ -437,7 +453,7 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
                 b.n_tiles_a = (int)(s->nb_pad / kTileCols);
                 b.n_tiles = (int)((s->nb_pad + s->nn_pad) / kTileCols);
                 b.exA_lo = s->exP_lo; b.exA_len = s->exP_len; b.exB_lo = s->exN_lo; b.exB_len = s->exN_len;
-                b.n_split = choose_split(s, a.n_rows, b.n_tiles, diff_rows_per_block());
+                b.n_split = choose_split(s, a.n_rows, b.n_tiles, diff_rows_per_block(diff_energy));
             }
             b.gate_skip_mask = kGateDone | (o.phase_switch ? kGatePhase64 : 0);
             const bool timed = s->timing && !f64_launch && s->tev_used + 2 <= (int)s->tev.size();
@@ -450,18 +466,19 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
             if (diff_energy) split_pot = b.n_split;
         }
         const int nb = (int)nblk(a.n_rows, kFinRows);
-        finalize_rows_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, split_pot, split_f64, split_mx,
+        finalize_rows_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, split_pot, split_f64, split_mx, fuse_static ? 1 : 0,
                                                        o.gate, o.phase_switch ? 1 : 0, s->part, a.part_stride,
                                                        s->row_site, s->r, dcmp, s->row_qs, s->row_k,
                                                        s->th_ptr, s->th_row, s->th_u,
                                                        (o.want_energy && !diff_energy) ? s->phi_static : nullptr, o.want_grad, gcmp, s->eblock);
-        // eblock comps (inter, intra, self, g2) -> energy[INTER..GNORM2], contiguous by design
-        reduce_blocks_kernel<<<1, 256, 0, st>>>(nb, 4, s->eblock, e + UPOL_E_INTER, 1);
+        // eblock comps (inter, intra, self, g2, static) -> energy[INTER..STATIC], contiguous by design
+        reduce_blocks_kernel<<<1, 256, 0, st>>>(nb, kEblockComps, s->eblock, e + UPOL_E_INTER, 1);
         UPOL_CUDA(cudaGetLastError());
     }
     // static partial of this rank's rows, then (sharded runs) one all-reduce of the vector
     const bool reduce = o.reduce_ranks && s->nranks > 1;
-    assemble_energy_kernel<<<1, 32, 0, st>>>(e, s->e_static, o.want_energy && !diff_energy, !reduce);
+    assemble_energy_kernel<<<1, 32, 0, st>>>(e, s->e_static, o.want_energy && !diff_energy, !reduce, fuse_static);
+    if (fuse_static) s->static_valid = true;
     if (reduce) {
         int rc = comm_allreduce_sum(s, e, UPOL_E_SIZE, st);
         if (rc) return rc;
@@ -564,7 +581,7 @@ int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream
     (void)r_dev_or_null;
     build_core_columns_kernel<<<nblk(std::max(s->na_pad, s->nm_pad), 256), 256, 0, st>>>(
         (int)s->nsite, (int)s->na_pad, s->r, s->qc, s->qs, s->centre[0], s->centre[1], s->centre[2], s->inv_grid,
-        s->mix_slot, (int)(s->nsite + s->nd), (int)s->nm_pad, s->cols, s->cols_f, s->cols_static);
+        s->mix_slot, (int)(s->nsite + s->nd), (int)s->nm_pad, s->cols, s->cols_f, s->cols_static, s->col_qeff);
     build_diff_columns_kernel<<<nblk(std::max<int64_t>(s->nsite, std::max(s->nb_pad, s->nn_pad)), 256), 256, 0, st>>>(
         (int)s->nsite, (int)s->nd, (int)s->nb_pad, (int)s->nn_pad, s->r, s->qc, s->site_row, s->site_nslot,
         s->centre[0], s->centre[1], s->centre[2], s->inv_grid, s->cols_x);
@@ -651,7 +668,7 @@ int sys_coulomb_static(upol_system *s, double *out2, cudaStream_t st) {
         a.exA_lo = ex; a.exA_len = ex + n; a.exB_lo = ex + 2 * n; a.exB_len = ex + 3 * n;
         a.cols = cols; a.n_tiles_a = ntile; a.n_tiles = ntile;
         a.n_split = split; a.part = part; a.part_stride = stride;
-        int rc = launch_pair_fp64(a, true, false, st);
+        int rc = launch_pair_fp64(a, true, false, false, st);
         if (rc) return rc;
         finalize_sites_kernel<<<nb, kFinBlock, 0, st>>>((int)n, split, part, stride, s->qc, s->qs, total, eblock);
         reduce_blocks_kernel<<<1, 256, 0, st>>>(nb, 1, eblock, out2 + total, 1);
@@ -821,7 +838,7 @@ int sys_core_forces(upol_system *s, const double *dcmp, double *dudr, cudaStream
             a.rx = s->rowx; a.ry = s->rowy; a.rz = s->rowz;
             a.cols = s->cols; a.n_tiles = (int)((s->na_pad + s->nb_pad) / kTileCols);
             a.n_split = choose_split(s, nr, a.n_tiles, fp64_rows_per_block());
-            int rc = launch_pair_fp64(a, false, true, st);
+            int rc = launch_pair_fp64(a, false, true, false, st);
             if (rc) return rc;
             fold_fields_kernel<3><<<nbf, kFinBlock, 0, st>>>((int)nr, (int)r_lo, nd, a.n_split, s->part, a.part_stride, 2, F);
         }
@@ -830,7 +847,7 @@ int sys_core_forces(upol_system *s, const double *dcmp, double *dudr, cudaStream
             a.rx = s->srowx; a.ry = s->srowy; a.rz = s->srowz;
             a.cols = s->cols_static; a.n_tiles = a.n_tiles_a;
             a.n_split = choose_split(s, nr, a.n_tiles, fp64_rows_per_block());
-            int rc = launch_pair_fp64(a, false, true, st);
+            int rc = launch_pair_fp64(a, false, true, false, st);
             if (rc) return rc;
             fold_fields_kernel<3><<<nbf, kFinBlock, 0, st>>>((int)nr, (int)r_lo, nd, a.n_split, s->part, a.part_stride, 2, H);
         }
