@@ -37,7 +37,7 @@ typedef struct upol_system upol_system;   /* one geometry + parameters resident 
 
 /* arithmetic modes */
 #define UPOL_FP64  0   /* fp64 pair math (reference runs JAX x64, polarization.py:196)        */
-#define UPOL_MIXED 1   /* fp32 pair math, fp64 accumulation                                   */
+#define UPOL_MIXED 1   /* fp32 pair math in difference form, fp64 accumulation (energy and field) */
 
 /* minimiser methods */
 #define UPOL_LBFGS 0   /* limited-memory BFGS, H0 = diag(1/k), derivative-driven line search  */
@@ -113,14 +113,17 @@ int upol_system_set_row_range(upol_system *sys, int64_t mol_lo, int64_t mol_hi);
  * jax.grad(Uind, argnums=1) taken inside jaxopt.BFGS (polarization.py:172-179).
  *   d[nsite*3]      Drude displacements, reference layout (values on non-polarisable sites are
  *                   ignored, as in the reference where they multiply a zero shell charge)
- *   energy[UPOL_E_SIZE]  may be NULL (gradient only: no potential pass, no static part)
+ *   energy[UPOL_E_SIZE]  may be NULL (gradient only: field pass, no potentials)
  *   grad[nsite*3]        may be NULL (energy only)
- * precision selects the arithmetic of the FIELD (gradient).  The potential (energy) is always
- * accumulated from fp64 pair terms: U_ind is the small difference U_coul - U_coul_static of two
- * large sums and fp32 pair terms cannot deliver it to 1e-5 ("mixed mode").  When the
- * energy is requested as well, the fp64 kernel produces the field in the same pass (cheaper than an
- * extra fp32 pass), so UPOL_MIXED changes the arithmetic of field-only calls (energy == NULL) and of
- * the minimiser's iterations.
+ * precision selects the pair arithmetic.  UPOL_FP64: fp64 pair terms, one pass that also forms the
+ * d-independent static potential of the rows when it is not cached for the current geometry.  UPOL_MIXED:
+ * ONE fp32 pass for the energy AND the gradient, no fp64 pair kernel and no static pass: U_ind is the
+ * small difference U_coul - U_coul_static of two large sums, so the pair terms are evaluated in the
+ * cancellation-free difference form f(A) - f(R) = (|R|^2-|A|^2)/(|A||R|(|A|+|R|)) on exact fixed-point
+ * coordinate differences, with fp64 accumulation per 128-column tile (csrc/pair_diff.cu); energies and
+ * gradients agree with UPOL_FP64 to 1e-5 relative (measured ~1e-8 / 2e-6 on liquid boxes).  In mixed mode
+ * energy[UPOL_E_STATIC] is not formed (0).  Zero-distance rule of all kernels: an inter-molecular 1/r term
+ * is dropped when r < 1e-5 nm (the reference: r == 0 exactly, polarization.py:33-42).
  */
 int upol_uind_energy_grad_dev(upol_system *sys, const double *d, int precision,
                               double *energy, double *grad, void *stream);
@@ -142,6 +145,10 @@ int upol_uind_core_gradient_dev(upol_system *sys, const double *d, double *dudr,
  *   out[1] = K sum_{i<j, inter} (qc+qs)_i (qc+qs)_j / R_ij      ( = Ucoul_static )
  */
 int upol_coulomb_static_dev(upol_system *sys, double *out2, void *stream);
+
+/* Uself = 1/2 sum_i k_i |d_i|^2 on plain DEVICE arrays d[n*3], k[n] (Uself, polarization.py:44-48); out[1].
+ * The same quantity is the UPOL_E_SELF component of an energy evaluation. */
+int upol_uself_dev(const double *d, const double *k, int64_t n, double *out, void *stream);
 
 /* Thole screening function on a dense array, S = 1-(1+u r/2)exp(-u r), r = |Rij|
  * (make_Sij, polarization.py:27-31).  rij[n*3], u[n] (or u[1] when u_is_scalar), out[n]. */
@@ -237,6 +244,10 @@ int upol_batched_minimize_dev(int device, int64_t nbatch, int64_t nsite,
  * kept between two calls.
  */
 int upol_system_set_kernel_timing(upol_system *sys, int enable);
+/* Kernels of this library launched on behalf of `sys` since it was created (energy/gradient evaluations,
+ * geometry uploads, minimiser slots; counted where they are enqueued).  bench.py reports the difference
+ * over its timed region as gpu_launches. */
+int64_t upol_system_launch_count(const upol_system *sys);
 int upol_system_kernel_time(upol_system *sys, double *ms_total, int32_t *launches);
 
 /* Periodic boundaries - an EXTENSION, not a replacement of reference code: shehan807/U_pol is gas

@@ -190,3 +190,48 @@ def test_plain_c_program_through_the_c_abi(tmp_path):
     k = np.where(qs != 0, K * qs**2 / 0.000978253, 0.0)
     _, info = UindSystem.from_compact(r, qc, qs, k, None).minimize(tol=1e-4)
     assert u == pytest.approx(info["U_ind"], rel=1e-8) and u < 0
+
+
+def test_one_pair_kernel_launch_per_evaluation():
+    """An evaluation is prepare -> ONE pair kernel -> finalize (its last block sums the energy vector) -> scatter:
+    the fp64 pass forms the static potential in the same launch (no separate static pass), and a mixed call
+    launches the difference-form kernel only (no fp64 pair kernel, no static pass)."""
+    s = synth.imidazole_box(20, seed=91)
+    D = synth.random_displacements(s, seed=92)
+    sys_ = UindSystem.from_drude_system(s)
+    d_dev = torch.as_tensor(D.reshape(-1)).cuda()
+    n0 = sys_.launch_count()
+    e64, g64 = sys_.energy_grad(d_dev)                       # static not cached yet: fused into the pass
+    n1 = sys_.launch_count()
+    assert n1 - n0 == 4
+    em, gm = sys_.energy_grad(d_dev, precision="mixed")
+    assert sys_.launch_count() - n1 == 4
+    assert abs(float(em[0]) - float(e64[0])) <= 1e-5 * abs(float(e64[0]))
+    assert float((gm - g64).abs().max()) <= 1e-5 * float(g64.abs().max())
+    # the static potential was kept by the fused pass: the second fp64 evaluation gives the same bits
+    e2, g2 = sys_.energy_grad(d_dev)
+    assert torch.equal(g2, g64) and abs(float(e2[0]) - float(e64[0])) <= 1e-13 * abs(float(e64[0]))
+    assert float(e2[5]) == float(e64[5]) != 0.0              # E_STATIC reported either way
+
+
+def test_dense_wrappers_reuse_the_device_system():
+    """drudeOpt followed by Uind on the same dense inputs (the reference's main(), polarization.py:246-257)
+    builds ONE device system."""
+    from u_pol_b200 import polarization as pol
+    from u_pol_b200 import util
+
+    s = synth.imidazole_box(3, seed=93)
+    Rij, _ = util.get_Rij_Dij(s)
+    Qi_core, Qi_shell, Qj_core, Qj_shell = util.get_QiQj(s)
+    k, u_scale = util.get_pol_params(s)
+    pol.clear_cache()
+    d_opt = pol.drudeOpt(Rij, np.zeros(3 * s.nmol * s.natoms), Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k)
+    assert len(pol._CACHE) == 1
+    first = next(iter(pol._CACHE.values()))
+    e = pol.Uind(Rij, d_opt, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k)
+    assert len(pol._CACHE) == 1 and next(iter(pol._CACHE.values())) is first
+    assert float(e) < 0
+    us = float(pol.Uself(d_opt, k))
+    assert us == pytest.approx(0.5 * float((np.asarray(k).reshape(-1, 1) * d_opt.cpu().numpy().reshape(-1, 3) ** 2).sum()), rel=1e-12)
+    pol.clear_cache()
+    assert not pol._CACHE

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libupol_b200.so")
 E_UIND, E_INTER, E_INTRA, E_SELF, E_GNORM2, E_STATIC, E_SIZE = 0, 1, 2, 3, 4, 5, 8
 FP64, MIXED = 0, 1
 LBFGS, CG = 0, 1
-FLAG_NOT_CONVERGED, FLAG_NONFINITE, FLAG_LINESEARCH = 1, 2, 4
+FLAG_NOT_CONVERGED, FLAG_NONFINITE, FLAG_LINESEARCH, FLAG_COMM = 1, 2, 4, 8
 COMM_ID_BYTES = 128
 P2P_EXPORT_BYTES = 192
 
@@ -53,6 +53,7 @@ _SIGNATURES = {
     "upol_uind_energy_grad_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "upol_uind_core_gradient_dev": (C.c_int, [_P, _P, _P, _P]),
     "upol_coulomb_static_dev": (C.c_int, [_P, _P, _P]),
+    "upol_uself_dev": (C.c_int, [_P, _P, _I64, _P, _P]),
     "upol_make_sij_dev": (C.c_int, [_P, _P, C.c_int, _I64, _P, _P]),
     "upol_min_options_default": (None, [C.POINTER(MinOptions)]),
     "upol_minimize_dev": (C.c_int, [_P, _P, C.POINTER(MinOptions), C.POINTER(MinResult), _P]),
@@ -65,6 +66,7 @@ _SIGNATURES = {
     "upol_batched_minimize_dev": (C.c_int, [C.c_int, _I64, _I64, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P,
                                             C.c_double, C.c_int32, _P, _P, _P]),
     "upol_system_set_kernel_timing": (C.c_int, [_P, C.c_int]),
+    "upol_system_launch_count": (_I64, [_P]),
     "upol_system_kernel_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "upol_measure_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "upol_system_set_periodic": (C.c_int, [_P, _P, C.c_double, C.c_int32]),
@@ -89,6 +91,22 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = handle
     return _lib
+
+
+def check_min_flags(flags, what="minimisation"):
+    """Minimiser flags (UPOL_FLAG_*): a lost peer or a non-finite gradient means the returned displacements
+    are not a minimum - raise; an unconverged run or an exhausted line search is reported as a warning."""
+    import warnings
+
+    if flags & FLAG_COMM:
+        raise UpolError(f"{what}: a peer rank did not deliver within the time-out (UPOL_FLAG_COMM); result invalid")
+    if flags & FLAG_NONFINITE:
+        raise UpolError(f"{what}: non-finite gradient (UPOL_FLAG_NONFINITE) - polarisation catastrophe or bad input")
+    if flags & FLAG_NOT_CONVERGED:
+        warnings.warn(f"{what}: not converged to the requested tolerance (UPOL_FLAG_NOT_CONVERGED)", RuntimeWarning)
+    elif flags & FLAG_LINESEARCH:
+        warnings.warn(f"{what}: a line search hit its step limit (UPOL_FLAG_LINESEARCH)", RuntimeWarning)
+    return flags
 
 
 def check(rc, what=""):

@@ -41,10 +41,10 @@ void free_system(upol_system *s) {
     comm_destroy(s);
     void *ptrs[] = {s->r, s->qc, s->qs, s->k, s->row_site, s->row_qs, s->row_k, s->exA_lo, s->exA_len,
                     s->exB_lo, s->exB_len, s->rowx, s->rowy, s->rowz, s->srowx, s->srowy, s->srowz,
-                    s->cols, s->cols_f, s->mix_slot, s->exM_lo, s->exM_len, s->cols_static, s->th_ptr, s->th_row, s->th_u, s->part, s->dc,
+                    s->cols, s->cols_static, s->th_ptr, s->th_row, s->th_u, s->part, s->dc,
                     s->gc, s->eblock, s->energy, s->e_static, s->phi_static, s->site_row,
                     s->cols_dcore, s->site_x, s->exS_lo, s->cf_tmp,
-                    s->cols_x, s->cols_d, s->cols_d2, s->col_qeff, s->site_nslot, s->exP_lo, s->exP_len, s->exN_lo, s->exN_len};
+                    s->cols_x, s->cols_d, s->cols_d2, s->col_qeff, s->ticket, s->site_nslot, s->exP_lo, s->exP_len, s->exN_lo, s->exN_len};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (s->pin) cudaFreeHost(s->pin);
     if (s->hscratch) cudaFree(s->hscratch);
@@ -139,15 +139,12 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
     s->nd_pad = round_up(std::max<int64_t>(s->nd, 1), 512);
     s->na_pad = round_up(nsite, kTileCols);
     s->nb_pad = round_up(std::max<int64_t>(s->nd, 1), kTileCols);
-    s->nm_pad = round_up(nsite + s->nd, kTileCols);
     s->nn_pad = round_up(std::max<int64_t>(nsite - s->nd, 1), kTileCols);
     s->mol_lo = 0; s->mol_hi = s->nmol; s->row_lo = 0; s->row_hi = s->nd;
 
     // per-row tables
     std::vector<int32_t> exA_lo(s->nd_pad, 0), exA_len(s->nd_pad, 0), exB_lo(s->nd_pad, 0), exB_len(s->nd_pad, 0);
     std::vector<double> row_qs(std::max<int64_t>(s->nd, 1), 0.0), row_k(std::max<int64_t>(s->nd, 1), 0.0);
-    std::vector<int32_t> mix_slot(nsite), exM_lo(s->nd_pad, 0), exM_len(s->nd_pad, 0);
-    for (int64_t i = 0, slot = 0; i < nsite; ++i) { mix_slot[i] = (int32_t)slot; slot += (s->h_site_row[i] >= 0) ? 2 : 1; }
     // difference-form mixed kernel: non-polarisable sites get slots of section N in site order
     std::vector<int32_t> site_nslot(nsite, -1), mol_n0(s->nmol, 0), mol_nn(s->nmol, 0);
     {
@@ -166,8 +163,6 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
         exP_len[i] = s->h_mol_nrow[m];
         exN_lo[i] = (int32_t)s->nb_pad + mol_n0[m];              // concatenated column index
         exN_len[i] = mol_nn[m];
-        exM_lo[i] = mix_slot[s->h_mol_site0[m]];
-        exM_len[i] = s->h_mol_nsite[m] + s->h_mol_nrow[m];
         exA_lo[i] = s->h_mol_site0[m];
         exA_len[i] = s->h_mol_nsite[m];
         exB_lo[i] = (int32_t)s->na_pad + s->h_mol_row0[m];   // concatenated column index
@@ -217,8 +212,6 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
     TRY(dev_alloc(&s->rowx, s->nd_pad)); TRY(dev_alloc(&s->rowy, s->nd_pad)); TRY(dev_alloc(&s->rowz, s->nd_pad));
     TRY(dev_alloc(&s->srowx, s->nd_pad)); TRY(dev_alloc(&s->srowy, s->nd_pad)); TRY(dev_alloc(&s->srowz, s->nd_pad));
     TRY(dev_alloc(&s->cols, s->na_pad + s->nb_pad));
-    TRY(dev_alloc(&s->cols_f, s->nm_pad));
-    TRY(dev_alloc(&s->mix_slot, nsite)); TRY(dev_alloc(&s->exM_lo, s->nd_pad)); TRY(dev_alloc(&s->exM_len, s->nd_pad));
     TRY(dev_alloc(&s->cols_static, s->na_pad)); TRY(dev_alloc(&s->col_qeff, s->na_pad));
     TRY(dev_alloc(&s->cols_x, s->nb_pad + s->nn_pad)); TRY(dev_alloc(&s->cols_d, s->nb_pad)); TRY(dev_alloc(&s->cols_d2, s->nb_pad));
     TRY(dev_alloc(&s->site_nslot, nsite));
@@ -230,6 +223,7 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
     TRY(dev_alloc(&s->dc, 3 * s->nd)); TRY(dev_alloc(&s->gc, 3 * s->nd));
     s->n_eblock = (int)((std::max<int64_t>(s->nd, nsite) + 31) / 32) + 1;   // finalize blocks hold 32 rows
     TRY(dev_alloc(&s->eblock, 5 * (size_t)s->n_eblock));   // kEblockComps per finalize block
+    TRY(dev_alloc(&s->ticket, 4));
     TRY(dev_alloc(&s->energy, UPOL_E_SIZE)); TRY(dev_alloc(&s->e_static, 2)); TRY(dev_alloc(&s->phi_static, s->nd_pad));
 
     {
@@ -249,9 +243,6 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
         cp(s->exA_len, exA_len.data(), sizeof(int32_t) * s->nd_pad);
         cp(s->exB_lo, exB_lo.data(), sizeof(int32_t) * s->nd_pad);
         cp(s->exB_len, exB_len.data(), sizeof(int32_t) * s->nd_pad);
-        cp(s->mix_slot, mix_slot.data(), sizeof(int32_t) * nsite);
-        cp(s->exM_lo, exM_lo.data(), sizeof(int32_t) * s->nd_pad);
-        cp(s->exM_len, exM_len.data(), sizeof(int32_t) * s->nd_pad);
         cp(s->site_nslot, site_nslot.data(), sizeof(int32_t) * nsite);
         cp(s->exP_lo, exP_lo.data(), sizeof(int32_t) * s->nd_pad);
         cp(s->exP_len, exP_len.data(), sizeof(int32_t) * s->nd_pad);
@@ -260,6 +251,7 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
         cp(s->th_ptr, th_ptr.data(), sizeof(int32_t) * (s->nd + 1));
         cp(s->th_row, th_row.data(), sizeof(int32_t) * th_row.size());
         cp(s->th_u, th_u.data(), sizeof(double) * th_u.size());
+        if (e == cudaSuccess) e = cudaMemset(s->ticket, 0, sizeof(int) * 4);
         if (e == cudaSuccess) e = cudaMemset(s->rowx, 0, sizeof(double) * s->nd_pad);
         if (e == cudaSuccess) e = cudaMemset(s->rowy, 0, sizeof(double) * s->nd_pad);
         if (e == cudaSuccess) e = cudaMemset(s->rowz, 0, sizeof(double) * s->nd_pad);
@@ -357,13 +349,12 @@ int upol_uind_energy_grad_dev(upol_system *s, const double *d, int precision, do
     if (!s || !d || (!energy && !grad)) return UPOL_ERR_ARG;
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = sys_gather_d(s, d, s->dc, st);
-    if (rc) return rc;
     EvalOpts o;
     o.precision = precision;
     o.want_grad = grad != nullptr;
     o.want_energy = energy != nullptr;      // NULL: field pass only (what a minimiser iteration needs)
-    rc = sys_eval_compact(s, s->dc, o, energy, s->gc, st);
+    o.d_full = d;                           // gathered into s->dc by the prepare kernel
+    int rc = sys_eval_compact(s, s->dc, o, energy, s->gc, st);
     if (rc) return rc;
     if (grad) {
         if (s->nranks > 1) { rc = comm_allgather_rows(s, s->gc, st); if (rc) return rc; }
@@ -396,6 +387,8 @@ int upol_uind_energy_grad_host(upol_system *s, const double *d, int precision, d
     if (grad && !g_pin) memcpy(grad, pg, sizeof(double) * n3);
     return UPOL_OK;
 }
+
+int64_t upol_system_launch_count(const upol_system *s) { return s ? s->launches : 0; }
 
 int upol_system_set_kernel_timing(upol_system *s, int enable) {
     if (!s) return UPOL_ERR_ARG;
@@ -445,6 +438,11 @@ static int upol_coulomb_static_dev_impl(upol_system *s, double *out2, void *stre
     if (!s || !out2 || s->ewald) return UPOL_ERR_ARG;           // open boundaries only
     DeviceGuard guard(s->device);
     return sys_coulomb_static(s, out2, (cudaStream_t)stream);
+}
+
+int upol_uself_dev(const double *d, const double *k, int64_t n, double *out, void *stream) {
+    if (!d || !k || !out || n < 0) return UPOL_ERR_ARG;
+    return sys_uself(d, k, n, out, (cudaStream_t)stream);
 }
 
 int upol_make_sij_dev(const double *rij, const double *u, int u_is_scalar, int64_t n, double *out, void *stream) {

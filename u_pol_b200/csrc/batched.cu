@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "thole.cuh"
 
 namespace upol {
 
@@ -37,29 +38,6 @@ struct BatchTopo {          // device pointers, shared by all systems
 __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-
-// grad grad g (see minimize.cu::thole_hessian)
-__device__ void thole_hess(double x, double y, double z, double u, double G[3][3]) {
-    const double r2 = x * x + y * y + z * z;
-    if (r2 == 0.0) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) G[i][j] = 0.0; return; }
-    const double r = sqrt(r2), ex = exp(-u * r);
-    const double S = 1.0 - (1.0 + 0.5 * r * u) * ex, Sp = 0.5 * u * (1.0 + u * r) * ex, Spp = -0.5 * u * u * u * r * ex;
-    const double t = Sp * r - S;
-    const double c = t / (r2 * r), cpr = (Spp / r2 - 3.0 * t / (r2 * r2)) / r;
-    const double v[3] = {x, y, z};
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) G[i][j] = (i == j ? c : 0.0) + cpr * v[i] * v[j];
-}
-
-__device__ __forceinline__ void thole_gc(double x, double y, double z, double u, double &g, double &c) {
-    const double r2 = x * x + y * y + z * z;
-    if (r2 == 0.0) { g = 0.0; c = 0.0; return; }
-    const double rr = sqrt(r2), ex = exp(-u * rr);
-    const double S = 1.0 - (1.0 + 0.5 * rr * u) * ex, Sp = 0.5 * u * (1.0 + u * rr) * ex;
-    const double ir = 1.0 / rr;
-    g = S * ir;
-    c = (Sp * ir - S * ir * ir) * ir;
 }
 
 // Per-warp working set inside dynamic shared memory.
@@ -92,7 +70,7 @@ __device__ void eval_system(const BatchTopo &t, const WarpMem &m, const double *
             if (t.site_mol[j] == ma) continue;        // polarization.py:90-91
             const double ddx = m.r[3 * j] - sx, ddy = m.r[3 * j + 1] - sy, ddz = m.r[3 * j + 2] - sz;
             const double r2 = ddx * ddx + ddy * ddy + ddz * ddz;
-            if (r2 == 0.0) continue;                  // zero distance: dropped (:33-42)
+            if (r2 < kZeroR2) continue;               // zero distance: dropped (:33-42; rule in thole.cuh)
             const double inv = rsqrt(r2), tq = t.qc[j] * inv, w = tq * inv * inv;
             if (POT) pa += tq;
             fx += w * ddx; fy += w * ddy; fz += w * ddz;
@@ -103,7 +81,7 @@ __device__ void eval_system(const BatchTopo &t, const WarpMem &m, const double *
             const double ddx = (m.r[3 * sb] - xcur[3 * b]) - sx, ddy = (m.r[3 * sb + 1] - xcur[3 * b + 1]) - sy,
                          ddz = (m.r[3 * sb + 2] - xcur[3 * b + 2]) - sz;
             const double r2 = ddx * ddx + ddy * ddy + ddz * ddz;
-            if (r2 == 0.0) continue;
+            if (r2 < kZeroR2) continue;
             const double inv = rsqrt(r2), tq = t.row_qs[b] * inv, w = tq * inv * inv;
             if (POT) pb += tq;
             fx += w * ddx; fy += w * ddy; fz += w * ddz;
@@ -119,13 +97,13 @@ __device__ void eval_system(const BatchTopo &t, const WarpMem &m, const double *
             const double Ax = Rx + dx0, Ay = Ry + dy0, Az = Rz + dz0;
             const double Cx = Ax - bx, Cy = Ay - by, Cz = Az - bz;
             double gA, cA, gC, cC;
-            thole_gc(Ax, Ay, Az, u, gA, cA);
-            thole_gc(Cx, Cy, Cz, u, gC, cC);
+            thole_g(Ax, Ay, Az, u, gA, cA);
+            thole_g(Cx, Cy, Cz, u, gC, cC);
             const double qq = kCoulomb * qs * t.row_qs[b];
             if (POT) {
                 double gR, cR, gB, cB;
-                thole_gc(Rx, Ry, Rz, u, gR, cR);
-                thole_gc(Rx - bx, Ry - by, Rz - bz, u, gB, cB);
+                thole_g(Rx, Ry, Rz, u, gR, cR);
+                thole_g(Rx - bx, Ry - by, Rz - bz, u, gB, cB);
                 ea += 0.5 * qq * (gR - gA - gB + gC);
             }
             gx += qq * (cC * Cx - cA * Ax); gy += qq * (cC * Cy - cA * Ay); gz += qq * (cC * Cz - cA * Az);
@@ -146,7 +124,7 @@ __device__ double static_part(const BatchTopo &t, const WarpMem &m, const double
             if (t.site_mol[j] == ma) continue;
             const double ddx = m.r[3 * j] - m.r[3 * sa], ddy = m.r[3 * j + 1] - m.r[3 * sa + 1], ddz = m.r[3 * j + 2] - m.r[3 * sa + 2];
             const double r2 = ddx * ddx + ddy * ddy + ddz * ddz;
-            if (r2 == 0.0) continue;
+            if (r2 < kZeroR2) continue;
             ph += (t.qc[j] + 0.5 * site_qs[j]) * rsqrt(r2);
         }
         e = -kCoulomb * t.row_qs[lane] * ph;
@@ -185,7 +163,7 @@ __global__ void batched_bfgs_kernel(BatchTopo t, const double *__restrict__ site
         for (int q = t.th_ptr[a]; q < t.th_ptr[a + 1]; ++q) {
             const int b = t.th_row[q], sb = t.row_site[b];
             double G[3][3];
-            thole_hess(m.r[3 * sb] - m.r[3 * sa], m.r[3 * sb + 1] - m.r[3 * sa + 1], m.r[3 * sb + 2] - m.r[3 * sa + 2], t.th_u[q], G);
+            thole_hessian(m.r[3 * sb] - m.r[3 * sa], m.r[3 * sb + 1] - m.r[3 * sa + 1], m.r[3 * sb + 2] - m.r[3 * sa + 2], t.th_u[q], G);
             const double qq = -kCoulomb * t.row_qs[a] * t.row_qs[b];
             for (int i = 0; i < 3; ++i)
                 for (int j = 0; j < 3; ++j) m.H[(3 * a + i) * n + 3 * b + j] = qq * G[i][j];
@@ -330,9 +308,20 @@ static int batched_minimize_impl(int device, int64_t nbatch, int64_t nsite, cons
         !energy_dev || npair < 0)
         return UPOL_ERR_ARG;
     if (nbatch == 0) return UPOL_OK;
-    int prev = -1;
-    cudaGetDevice(&prev);
-    if (prev != device && cudaSetDevice(device) != cudaSuccess) { set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__); return UPOL_ERR_CUDA; }
+    // scratch + device switch undone on EVERY exit path (early CUDA errors included)
+    struct Scope {
+        int prev = -1, dev = -1;
+        double *dblob = nullptr;
+        int *iblob = nullptr;
+        ~Scope() {
+            if (dblob) cudaFree(dblob);
+            if (iblob) cudaFree(iblob);
+            if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+        }
+    } scope;
+    scope.dev = device;
+    cudaGetDevice(&scope.prev);
+    if (scope.prev != device && cudaSetDevice(device) != cudaSuccess) { set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__); return UPOL_ERR_CUDA; }
     cudaStream_t st = (cudaStream_t)stream;
 
     // host topology -> compact tables
@@ -365,10 +354,10 @@ static int batched_minimize_impl(int device, int64_t nbatch, int64_t nsite, cons
     // one device blob for the topology
     const size_t nd1 = std::max(nd, 1), np1 = std::max<size_t>(th_row.size(), 1);
     const size_t dbl = nsite + nd1 + nd1 + np1 + nsite, itg = nd1 + nsite + (nd + 1) + np1;
-    double *dblob = nullptr;
-    int *iblob = nullptr;
-    UPOL_CUDA(cudaMalloc((void **)&dblob, dbl * sizeof(double)));
-    UPOL_CUDA(cudaMalloc((void **)&iblob, itg * sizeof(int)));
+    UPOL_CUDA(cudaMalloc((void **)&scope.dblob, dbl * sizeof(double)));
+    UPOL_CUDA(cudaMalloc((void **)&scope.iblob, itg * sizeof(int)));
+    double *dblob = scope.dblob;
+    int *iblob = scope.iblob;
     std::vector<double> hd;
     hd.insert(hd.end(), q_core, q_core + nsite);
     hd.insert(hd.end(), row_qs.begin(), row_qs.end()); hd.resize(nsite + nd1, 0.0);
@@ -393,7 +382,7 @@ static int batched_minimize_impl(int device, int64_t nbatch, int64_t nsite, cons
     const size_t per_warp_bytes = (size_t)per_warp * sizeof(double);
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    if (per_warp_bytes > (size_t)max_smem) { cudaFree(dblob); cudaFree(iblob); return UPOL_ERR_ARG; }
+    if (per_warp_bytes > (size_t)max_smem) return UPOL_ERR_ARG;
     int wpb = (int)std::min<size_t>(8, std::max<size_t>(1, (size_t)(48 * 1024) / per_warp_bytes));
     const size_t smem = per_warp_bytes * wpb;
     if (smem > 48 * 1024)
@@ -402,9 +391,7 @@ static int batched_minimize_impl(int device, int64_t nbatch, int64_t nsite, cons
     batched_bfgs_kernel<<<blocks, 32 * wpb, smem, st>>>(t, site_qs_dev, nbatch, r_core_dev, d_dev, tol, maxiter,
                                                        energy_dev, iterations_dev, wpb, per_warp);
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);     // the topology blobs die here
-    cudaFree(dblob); cudaFree(iblob);
-    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);     // the topology blobs die with `scope`
     if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
     return UPOL_OK;
 }

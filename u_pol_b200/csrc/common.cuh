@@ -48,7 +48,7 @@ struct PairArgs {
     const int *exA_lo, *exA_len;  // excluded column interval inside section A (per row)
     const int *exB_lo, *exB_len;  // excluded column interval inside section B (per row, already offset)
     // columns: concatenated, each section padded to a multiple of kTileCols
-    const void *cols;           // double4* (fp64): x, y, z, q;  int4* (mixed): fixed-point x, y, z + float q bits
+    const void *cols;           // double4* (fp64): x, y, z, q;  int4* (mixed, sections P|N): fixed-point x, y, z + float q bits
     const void *cols_b;         // optional: section B lives in a separate array (else it follows A)
     int n_tiles_a;              // tiles in section A (cores)
     int n_tiles;                // total tiles (A then B)
@@ -70,13 +70,11 @@ struct PairArgs {
     int gate_skip_mask;
 };
 
-constexpr int kRowsMixed = 4;
 // gate bits written by the minimiser's control kernel
 constexpr int kGateDone = 1, kGatePhase64 = 2, kGatePhaseMixed = 4;
 constexpr int kMaxPack = 17 * 8;   // (max history + 1) x values per slot of the minimiser's scalar pack
 
 int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, bool fuse_static, cudaStream_t st);
-int launch_pair_mixed(const PairArgs &a, cudaStream_t st);
 int launch_pair_diff(const PairArgs &a, bool with_pot, cudaStream_t st);
 int diff_rows_per_block(bool with_pot);
 int launch_pair_fp64_two_fields(const PairArgs &a, cudaStream_t st);
@@ -110,11 +108,6 @@ struct upol_system {
     double *srowx = nullptr, *srowy = nullptr, *srowz = nullptr;  // [nd_pad] Drude core positions
     // device: columns
     double4 *cols = nullptr;      // [na_pad + nb_pad]  cores (x,y,z,qc) | shells (x,y,z,qs)
-    int4 *cols_f = nullptr;       // [nm_pad] mixed kernel: fixed point about the box centre (+ float q bits),
-                                  // ONE section, core and shell of a site adjacent (see pair_kernels.cu)
-    int *mix_slot = nullptr;      // [nsite] column slot of a site's core in cols_f (its shell is slot+1)
-    int *exM_lo = nullptr, *exM_len = nullptr;   // [nd_pad] excluded interval of a row in cols_f
-    int64_t nm_pad = 0;
     // mixed mode, difference form (pair_diff.cu): section P = polarisable sites in Drude-row order (nb_pad
     // slots), section N = the other sites (nn_pad slots)
     int4 *cols_x = nullptr;       // [nb_pad + nn_pad] fixed-point core position, float bits of q_core
@@ -138,6 +131,8 @@ struct upol_system {
     double *gc = nullptr;         // [nd*3] compact gradient
     double *eblock = nullptr;     // per-block energy partials
     int n_eblock = 0;
+    int *ticket = nullptr;        // [4] device: block-completion counter of the finalize kernel (self-resetting)
+    int64_t launches = 0;         // kernels of this library launched for this system (bench.py's gpu_launches)
     double *energy = nullptr;     // [UPOL_E_SIZE] device result of the last evaluation
     double *e_static = nullptr;   // [2] device: d-independent part summed over rows (informational)
     double *phi_static = nullptr; // [nd_pad] device: per-row static potential, subtracted row by row
@@ -196,6 +191,7 @@ struct EvalOpts {
     bool reduce_ranks = true;      // all-reduce the energy vector over ranks (sharded runs)
     const int *gate = nullptr;     // minimiser gate word (see kGate*)
     bool phase_switch = false;     // minimiser: launch both field kernels, gate picks one
+    const double *d_full = nullptr; // displacements in the (nsite,3) layout: gathered into s->dc by the prepare kernel
 };
 int sys_eval_compact(upol_system *s, const double *d_compact, const EvalOpts &o,
                      double *energy_dev, double *grad_compact, cudaStream_t st);
@@ -209,6 +205,7 @@ int choose_split(const upol_system *s, int64_t n_rows, int n_tiles, int rows_per
 int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream_t st);
 void set_box(upol_system *s, const double *lo, const double *hi);
 int sys_box_from_device(upol_system *s, cudaStream_t st);
+int sys_uself(const double *d, const double *k, int64_t n, double *out, cudaStream_t st);
 int sys_make_sij(const double *rij, const double *u, int u_is_scalar, int64_t n, double *out, cudaStream_t st);
 int sys_coulomb_static(upol_system *s, double *out2, cudaStream_t st);
 int sys_core_forces(upol_system *s, const double *d_compact, double *dudr_full, cudaStream_t st);

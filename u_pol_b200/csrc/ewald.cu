@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "thole.cuh"
 
 namespace upol {
 
@@ -55,7 +56,6 @@ namespace {
 
 constexpr int kSfacChunks = 16;       // charge chunks of the structure-factor pass (partials per k)
 constexpr int kRun = 16;              // reciprocal vectors per run of consecutive n_z (rows kernel)
-constexpr double kZeroR2 = 1e-10;     // (1e-5 nm)^2: coincident pair, term dropped (polarization.py:33-42)
 
 // nearest image: dx - L * round(dx / L); the round-to-nearest-integer is the add/subtract of 1.5 * 2^52
 // (two full-rate DADDs, exact for |dx / L| < 2^51) instead of FRND.F64, which is a conversion-pipe op
@@ -479,7 +479,8 @@ int ewald_setup(upol_system *s, const double *box, double kappa, int nmax) {
         cudaMemcpy(e->kn, kn.data(), sizeof(int4) * e->nk_pad, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(e->kA, kA.data(), sizeof(double) * e->nk_pad, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(e->mol_site0, s->h_mol_site0.data(), sizeof(int) * s->nmol, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(e->mol_nsite, s->h_mol_nsite.data(), sizeof(int) * s->nmol, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaMemcpy(e->mol_nsite, s->h_mol_nsite.data(), sizeof(int) * s->nmol, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess) {      // pageable copies on the legacy stream must land before use on any stream
         set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
         return fail(UPOL_ERR_CUDA);
     }

@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "thole.cuh"
 
 namespace upol {
 
@@ -77,21 +78,6 @@ void ws_free(MinWs *w) {
     if (w->h_sc) cudaFreeHost(w->h_sc);
     for (auto &e : w->ev) if (e) cudaEventDestroy(e);
     delete w;
-}
-
-// Second derivative tensor of g(x) = S(u|x|)/|x| (make_Sij, polarization.py:27-31):
-//   grad g = c(r) x,  c = (S' r - S)/r^3;   grad grad g = c I + (c'/r) x x^T,
-//   c' = S''/r^2 - 3 (S' r - S)/r^4,  S' = u(1+ur)e^{-ur}/2,  S'' = -u^3 r e^{-ur}/2.
-__device__ void thole_hessian(double x, double y, double z, double u, double G[3][3]) {
-    const double r2 = x * x + y * y + z * z;
-    if (r2 == 0.0) { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) G[i][j] = 0.0; return; }
-    const double r = sqrt(r2), ex = exp(-u * r);
-    const double S = 1.0 - (1.0 + 0.5 * r * u) * ex, Sp = 0.5 * u * (1.0 + u * r) * ex, Spp = -0.5 * u * u * u * r * ex;
-    const double t = Sp * r - S;
-    const double c = t / (r2 * r), cpr = (Spp / r2 - 3.0 * t / (r2 * r2)) / r;
-    const double v[3] = {x, y, z};
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) G[i][j] = (i == j ? c : 0.0) + cpr * v[i] * v[j];
 }
 
 // One thread per molecule: block Hessian of (springs + Thole intra pairs) at d = 0, inverted in
@@ -261,10 +247,8 @@ dots_kernel(int m, int64_t n, int64_t e0, int64_t e1, const int *__restrict__ ic
 // One block.  Without peers: pack = sum of the block partials.  With peers: the local sums go into
 // every rank's mailbox slot of this rank over NVLink, then the arrival flag of this rank is raised on
 // every peer (fence, then flag); the controller below adds the mailboxes in rank order.
-__global__ void __launch_bounds__(kMaxPack + 24)
-dots_reduce_kernel(int m, int nblocks, const int *__restrict__ ic, const double *__restrict__ partial,
-                   double *__restrict__ pack, P2P pp) {
-    if (ic[I_GATE] & kGateDone) return;
+__device__ __forceinline__ void reduce_partials(int m, int nblocks, const double *__restrict__ partial,
+                                                double *__restrict__ pack, const P2P &pp) {
     const int idx = threadIdx.x, len = (m + 1) * kDotVals;
     double t = 0.0;
     if (idx < len && (idx % kDotVals) < 6)
@@ -280,12 +264,26 @@ dots_reduce_kernel(int m, int nblocks, const int *__restrict__ ic, const double 
     if (idx < pp.nranks) *((volatile int *)(pp.peer_flags[idx] + pp.rank)) = pp.epoch;
 }
 
+// Stand-alone form, used when an NCCL all-reduce sits between the local sums and the controller.
+__global__ void __launch_bounds__(kMaxPack + 24)
+dots_reduce_kernel(int m, int nblocks, const int *__restrict__ ic, const double *__restrict__ partial,
+                   double *__restrict__ pack, P2P pp) {
+    if (ic[I_GATE] & kGateDone) return;
+    reduce_partials(m, nblocks, partial, pack, pp);
+}
+
 // Single-thread controller: line-search decision, history bookkeeping, m x m solves.
 __global__ void __launch_bounds__(kMaxPack + 24)
 control_kernel(int m, int maxiter, int mixed_enabled, int *__restrict__ ic, double *__restrict__ sc,
                double *__restrict__ pack, double *__restrict__ RS, double *__restrict__ YY,
-               double *__restrict__ coef, P2P pp) {
+               double *__restrict__ coef, P2P pp, int nblocks_reduce, const double *__restrict__ partial) {
     if (ic[I_GATE] & kGateDone) return;
+    if (nblocks_reduce > 0) {
+        // single rank or peer-memory exchange: the fold of the block partials happens here (one launch less)
+        reduce_partials(m, nblocks_reduce, partial, pack, pp);
+        __threadfence();
+        __syncthreads();
+    }
     if (pp.on) {
         // wait for every rank's partial sums, then add them in rank order: every rank gets the same bits
         __shared__ int bad;
@@ -557,6 +555,9 @@ static int ws_ensure(upol_system *s, int m, MinWs **out) {
             ok = ok && cudaMemcpy(w->mol_row0, s->h_mol_row0.data(), sizeof(int) * s->nmol, cudaMemcpyHostToDevice) == cudaSuccess;
             ok = ok && cudaMemcpy(w->mol_nrow, s->h_mol_nrow.data(), sizeof(int) * s->nmol, cudaMemcpyHostToDevice) == cudaSuccess;
             ok = ok && cudaMemcpy(w->row_mol, rmol.data(), sizeof(int) * rmol.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+            // pageable copies on the legacy stream: make sure they have landed before kernels on the caller's
+            // (possibly non-blocking) stream read the tables
+            ok = ok && cudaDeviceSynchronize() == cudaSuccess;
         }
         (void)max_rows;
     }
@@ -607,6 +608,13 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
     pp.peer_x = s->d_peer_x; pp.peer_pack = s->d_peer_pack; pp.peer_flags = s->d_peer_flags;
     pp.my_pack = s->xchg_pack; pp.my_flags = s->xchg_flags;
     int slots_in_call = 0;
+    if (pp.on) {
+        // Nothing else aligns the ranks when they enter this call, and the peer waits below give up after ~2 s:
+        // a host-side skew (data loading, a first-call set-up on one rank) must not be mistaken for a dead peer.
+        // One tiny NCCL all-reduce on the stream is a device-side barrier without a time-out.
+        rc = comm_allreduce_sum(s, w->pack, 1, st);
+        if (rc) return rc;
+    }
 
     auto enqueue_slot = [&]() -> int {
         if (pp.on) {
@@ -620,10 +628,17 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
         precond_apply_kernel<<<ublocks, 256, 0, st>>>(e0, e1, w->ic, w->row_mol, w->mol_row0, w->mol_nrow, w->blk_off,
                                                       w->blk, w->g, w->g0, w->Pg, w->Py);
         dots_kernel<<<dg, kDotBlock, 0, st>>>(m, n, e0, e1, w->ic, w->S, w->Y, w->g, w->g0, w->p, w->Pg, w->Py, w->partial);
-        dots_reduce_kernel<<<1, kMaxPack + 24, 0, st>>>(m, w->nblocks, w->ic, w->partial, w->pack, pp);
-        if (s->nranks > 1 && !pp.on) { r = comm_allreduce_sum(s, w->pack, (int64_t)(m + 1) * kDotVals, st); if (r) return r; }
-        control_kernel<<<1, kMaxPack + 24, 0, st>>>(m, o->maxiter, mixed ? 1 : 0, w->ic, w->sc, w->pack, w->RS, w->YY, w->coef, pp);
+        const bool nccl_between = s->nranks > 1 && !pp.on;
+        if (nccl_between) {
+            dots_reduce_kernel<<<1, kMaxPack + 24, 0, st>>>(m, w->nblocks, w->ic, w->partial, w->pack, pp);
+            r = comm_allreduce_sum(s, w->pack, (int64_t)(m + 1) * kDotVals, st);
+            if (r) return r;
+            ++s->launches;
+        }
+        control_kernel<<<1, kMaxPack + 24, 0, st>>>(m, o->maxiter, mixed ? 1 : 0, w->ic, w->sc, w->pack, w->RS, w->YY, w->coef, pp,
+                                                    nccl_between ? 0 : w->nblocks, w->partial);
         update_kernel<<<ublocks, 256, 0, st>>>(m, n, e0, e1, w->ic, w->sc, w->coef, w->S, w->Y, x, w->x0, w->g, w->g0, w->p, w->Pg, w->Py, pp);
+        s->launches += 4;
         if (s->nranks > 1 && !pp.on) { r = comm_allgather_rows(s, x, st); if (r) return r; }
         UPOL_CUDA(cudaGetLastError());
         return UPOL_OK;

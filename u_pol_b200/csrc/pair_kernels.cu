@@ -16,8 +16,7 @@
 //                                                     fields of the two column sections apart (core forces)
 //                                                     FUSE adds the static potential at the Drude cores (K3)
 //                                                     from the same core tiles, 10 DP ops per interaction
-//   pair_mixed_kernel<ROWS>                           field only: fixed-point coordinates, fp32 pair math,
-//                                                     fp64 accumulation
+// (the mixed-precision kernel lives in pair_diff.cu)
 //
 // Layout: columns are double4 (x, y, z, q), section A (cores) and section B (shells) each padded to
 // a tile multiple with zero-charge dummies, so a tile is never mixed and the 1/2 weight of shell
@@ -30,14 +29,9 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "thole.cuh"
 
 namespace upol {
-
-// High word of 1e-10 (nm^2): squared distances below it (r < 1e-5 nm, five orders of magnitude below any
-// physical contact) are treated as the reference's zero distance, whose term is dropped
-// (polarization.py:33-42).  One threshold for the direct and the expanded-square kernels; the latter
-// cannot tell an exact zero from its ~1e-14 cancellation noise.
-constexpr int kZeroR2Hi = 0x3DDB7CDF;
 
 // Compensated accumulation (Knuth two-sum) of a tile partial into a (hi, lo) pair.  The row
 // potentials reach ~2e4 e/nm at 100 k Drudes (all core charges positive, all shells negative) while
@@ -294,177 +288,6 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_fp64_kernel(const PairArgs 
     }
 }
 
-// Mixed mode (field only): fixed-point coordinates, fp32 pair arithmetic, fp64 accumulation.
-//
-// Positions are stored as 32-bit fixed point relative to the box centre (grid = 2^-k nm chosen
-// so the box fits in +-2^30).  Coordinate differences are then EXACT integer subtractions on the
-// integer pipe; only the difference is converted to fp32 (rel. error 2^-24 of the difference
-// itself, not of the box size).  This matters: each neighbour site contributes a core and a
-// shell term of opposite sign and ~5e3 kJ/mol/nm each that nearly cancel, so box-scale fp32
-// coordinates (ulp ~5e-7 nm) cost 1e-5 of the net gradient; fixed point keeps it ~1e-6.
-// Pair math (r^2, rsqrt, q/r^3, 3 FMAs) is fp32 in grid units; per-tile fp32 partial sums are
-// promoted to fp64 accumulators after every tile; the factor grid^-2 is applied once at the end.
-//
-// The potential is NOT formed here: U_ind is the small difference of two large sums
-// (U_coul - U_coul_static) and fp32 pair terms cannot deliver it to 1e-5 ("mixed
-// mode").  Energies always come from the fp64 kernel.
-__device__ __forceinline__ float rsqrt_f32(float x) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // bare MUFU.RSQ, no denormal fix-up
-    return y;
-}
-
-// q / r^3 from r^2: MUFU.RSQ seed y (rel. error eps <= 2^-22.9) and a first-order correction of
-// the CUBE, y^3 (1 + 1.5 e) with e = 1 - r2 y^2 = -2 eps + O(eps^2); 3 extra FMA-pipe ops bring the
-// 3 eps ~ 4e-7 error of y^3 down to fp32 rounding level.
-__device__ __forceinline__ float q_over_r3(float q, float r2) {
-    const float y = rsqrt_f32(r2);
-    const float y2 = y * y;
-    const float e = fmaf(-r2, y2, 1.0f);
-    const float z = (q * y) * y2;
-    return fmaf(z * e, 1.5f, z);
-}
-
-// Packed fp32 pairs (PTX f32x2, SASS FFMA2 / FMUL2; sm_100 and later).
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-
-template <int ROWS>
-__global__ void __launch_bounds__(kBlock) pair_mixed_kernel(const PairArgs a) {
-    static_assert(ROWS % 2 == 0, "rows are processed in fp32 pairs");
-    __shared__ int4 sh[kTileCols];
-    if (a.gate != nullptr && (*a.gate & a.gate_skip_mask) != 0) return;
-    const int4 *__restrict__ cols = static_cast<const int4 *>(a.cols);
-
-    const int tid = threadIdx.x;
-    const int row_base = blockIdx.x * (kBlock * ROWS) + tid;
-    int sx[ROWS], sy[ROWS], sz[ROWS];
-    int loA[ROWS], lenA[ROWS], loB[ROWS], lenB[ROWS];
-    double fx[ROWS], fy[ROWS], fz[ROWS];
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const int lr = row_base + r * kBlock;
-        const bool live = lr < a.n_rows;
-        const int i = a.row0 + (live ? lr : 0);
-        sx[r] = __double2int_rn((a.rx[i] - a.cx) * a.inv_grid);
-        sy[r] = __double2int_rn((a.ry[i] - a.cy) * a.inv_grid);
-        sz[r] = __double2int_rn((a.rz[i] - a.cz) * a.inv_grid);
-        loA[r] = a.exA_lo[i]; lenA[r] = a.exA_len[i];
-        loB[r] = a.exB_lo[i]; lenB[r] = a.exB_len[i];
-        fx[r] = fy[r] = fz[r] = 0.0;
-    }
-
-    const int t0 = (int)(((int64_t)a.n_tiles * blockIdx.y) / a.n_split);
-    const int t1 = (int)(((int64_t)a.n_tiles * (blockIdx.y + 1)) / a.n_split);
-
-    for (int t = t0; t < t1; ++t) {
-        const int base = t * kTileCols;
-        __syncthreads();
-        for (int j = tid; j < kTileCols; j += kBlock) sh[j] = cols[base + j];
-        __syncthreads();
-
-        const bool isB = t >= a.n_tiles_a;
-        bool need = false;
-        int lo[ROWS], len[ROWS];
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            lo[r] = (isB ? loB[r] : loA[r]) - base;
-            len[r] = isB ? lenB[r] : lenA[r];
-            need |= (lo[r] < kTileCols) && (lo[r] + len[r] > 0);
-        }
-        float gx[ROWS], gy[ROWS], gz[ROWS];
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) gx[r] = gy[r] = gz[r] = 0.f;
-
-        if (__any_sync(0xffffffffu, need)) {
-#pragma unroll 2
-            for (int j = 0; j < kTileCols; ++j) {
-                const int4 c = sh[j];
-                const float cq = __int_as_float(c.w);
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                    const float dx = (float)(c.x - sx[r]), dy = (float)(c.y - sy[r]), dz = (float)(c.z - sz[r]);
-                    const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, 1.0f)));
-                    const bool drop = (unsigned)(j - lo[r]) < (unsigned)len[r];
-                    const float q = drop ? 0.f : cq;
-                    const float w = q_over_r3(q, r2);
-                    gx[r] = fmaf(w, dx, gx[r]); gy[r] = fmaf(w, dy, gy[r]); gz[r] = fmaf(w, dz, gz[r]);
-                }
-            }
-        } else {
-            // Two rows per instruction: sm_100 executes fp32 pairs (FFMA2 / FMUL2) at the scalar FMA rate
-            // but in half the issue slots, and this loop is issue-bound.  Operation order and rounding
-            // are those of q_over_r3 (e is carried negated, which is exact), so both branches of this
-            // if give the same bits.
-            f32x2 hx[ROWS / 2], hy[ROWS / 2], hz[ROWS / 2];
-#pragma unroll
-            for (int p = 0; p < ROWS / 2; ++p) hx[p] = hy[p] = hz[p] = pack2(0.f, 0.f);
-            const f32x2 one2 = pack2(1.0f, 1.0f), mone2 = pack2(-1.0f, -1.0f), m15 = pack2(-1.5f, -1.5f);
-#pragma unroll 8
-            for (int j = 0; j < kTileCols; ++j) {
-                const int4 c = sh[j];
-                const float cq = __int_as_float(c.w);
-                const f32x2 cq2 = pack2(cq, cq);
-#pragma unroll
-                for (int p = 0; p < ROWS / 2; ++p) {
-                    const f32x2 dx = pack2((float)(c.x - sx[2 * p]), (float)(c.x - sx[2 * p + 1]));
-                    const f32x2 dy = pack2((float)(c.y - sy[2 * p]), (float)(c.y - sy[2 * p + 1]));
-                    const f32x2 dz = pack2((float)(c.z - sz[2 * p]), (float)(c.z - sz[2 * p + 1]));
-                    // +1 grid unit^2 (~1e-16 nm^2, < 1e-12 of any physical r^2) keeps 1/r finite for a
-                    // coincident pair, which has dx = dy = dz = 0 exactly and so adds w * 0 = 0
-                    // (zero distance -> term dropped) at no extra instruction
-                    const f32x2 r2 = fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, one2)));
-                    float r2a, r2b;
-                    unpack2(r2, r2a, r2b);
-                    const f32x2 y = pack2(rsqrt_f32(r2a), rsqrt_f32(r2b));
-                    const f32x2 y2 = mul2(y, y);
-                    const f32x2 me = fma2(r2, y2, mone2);              // -(1 - r2 y^2)
-                    const f32x2 z = mul2(mul2(cq2, y), y2);
-                    const f32x2 w = fma2(mul2(z, me), m15, z);
-                    hx[p] = fma2(w, dx, hx[p]); hy[p] = fma2(w, dy, hy[p]); hz[p] = fma2(w, dz, hz[p]);
-                }
-            }
-#pragma unroll
-            for (int p = 0; p < ROWS / 2; ++p) {
-                unpack2(hx[p], gx[2 * p], gx[2 * p + 1]);
-                unpack2(hy[p], gy[2 * p], gy[2 * p + 1]);
-                unpack2(hz[p], gz[2 * p], gz[2 * p + 1]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) { fx[r] += (double)gx[r]; fy[r] += (double)gy[r]; fz[r] += (double)gz[r]; }
-    }
-
-    const double scale = a.inv_grid * a.inv_grid;     // grid units -> nm^-2
-    double *out = a.part + (int64_t)blockIdx.y * kPartComps * a.part_stride;
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const int lr = row_base + r * kBlock;
-        if (lr < a.n_rows) {
-            out[2 * a.part_stride + lr] = fx[r] * scale;
-            out[3 * a.part_stride + lr] = fy[r] * scale;
-            out[4 * a.part_stride + lr] = fz[r] * scale;
-        }
-    }
-}
-
 template <int ROWS, int MINB>
 static void launch_fp64_variant(const PairArgs &a, bool with_pot, bool with_grad, bool fuse_static, cudaStream_t st) {
     dim3 grid((unsigned)((a.n_rows + kBlock * ROWS - 1) / (kBlock * ROWS)), (unsigned)a.n_split);
@@ -495,17 +318,6 @@ int launch_pair_fp64_two_fields(const PairArgs &a, cudaStream_t st) {
     if (a.n_rows <= 0) return UPOL_OK;
     dim3 grid((unsigned)((a.n_rows + kRowTile - 1) / kRowTile), (unsigned)a.n_split);
     pair_fp64_kernel<kRowsPerThread, false, true, 1, true><<<grid, kBlock, 0, st>>>(a);
-    UPOL_CUDA(cudaGetLastError());
-    return UPOL_OK;
-}
-
-int launch_pair_mixed(const PairArgs &a, cudaStream_t st) {
-    if (a.n_rows <= 0) return UPOL_OK;
-    // 2 or 4 rows per thread and 4-8 resident blocks all measure within 3 % (occupancy is not the
-    // limiter; after the f32x2 packing no single pipe is: FMA 64 %, ALU 57 %, XU 42 %, issue 69 %)
-    const int rows_per_block = kBlock * kRowsMixed;
-    dim3 grid((unsigned)((a.n_rows + rows_per_block - 1) / rows_per_block), (unsigned)a.n_split);
-    pair_mixed_kernel<kRowsMixed><<<grid, kBlock, 0, st>>>(a);
     UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
 }

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "thole.cuh"
 
 namespace upol {
 
@@ -35,17 +36,13 @@ __device__ __forceinline__ int4 fix_col(double x, double y, double z, double inv
 // Core columns (section A), static-pass columns and Drude core rows; once per geometry.
 __global__ void build_core_columns_kernel(int nsite, int na_pad, const double *__restrict__ r,
                                           const double *__restrict__ qc, const double *__restrict__ qs,
-                                          double cx, double cy, double cz, double inv_grid,
-                                          const int *__restrict__ mix_slot, int n_mix, int nm_pad,
-                                          double4 *__restrict__ cols, int4 *__restrict__ cols_f,
+                                          double4 *__restrict__ cols,
                                           double4 *__restrict__ cols_static, double *__restrict__ col_qeff) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nm_pad - n_mix) cols_f[n_mix + i] = make_int4(kFixFar, kFixFar, kFixFar, 0);   // tail padding
     if (i >= na_pad) return;
     if (i < nsite) {
         const double x = r[3 * i], y = r[3 * i + 1], z = r[3 * i + 2];
         cols[i] = make_double4(x, y, z, qc[i]);
-        cols_f[mix_slot[i]] = fix_col(x - cx, y - cy, z - cz, inv_grid, qc[i]);
         cols_static[i] = make_double4(x, y, z, qc[i] + 0.5 * qs[i]);
         col_qeff[i] = qc[i] + 0.5 * qs[i];
     } else {
@@ -80,24 +77,29 @@ __global__ void build_static_rows_kernel(int nd, const int *__restrict__ row_sit
 }
 
 // K4a: shell positions and shell columns (section B) from the current displacements.
+// With d_full != nullptr the displacements come in the reference's (nsite,3) layout and the compact copy dc
+// is written here as well (no separate gather launch).
 __global__ void prepare_shells_kernel(int nd, int nb_pad, const int *__restrict__ row_site,
-                                      const double *__restrict__ r, const double *__restrict__ dc,
-                                      const double *__restrict__ row_qs,
-                                      double cx, double cy, double cz, double inv_grid,
-                                      const int *__restrict__ mix_slot,
+                                      const double *__restrict__ r, const double *__restrict__ d_full, double *__restrict__ dc,
+                                      const double *__restrict__ row_qs, double inv_grid,
                                       double *__restrict__ rowx, double *__restrict__ rowy, double *__restrict__ rowz,
-                                      double4 *__restrict__ colsB, int4 *__restrict__ cols_f,
-                                      float4 *__restrict__ cols_d, float *__restrict__ cols_d2) {
+                                      double4 *__restrict__ colsB, float4 *__restrict__ cols_d, float *__restrict__ cols_d2) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb_pad) return;
     if (i < nd) {
         const int s = row_site[i];
-        const double x = r[3 * s] - dc[3 * i], y = r[3 * s + 1] - dc[3 * i + 1], z = r[3 * s + 2] - dc[3 * i + 2];
+        double ddx, ddy, ddz;
+        if (d_full != nullptr) {
+            ddx = d_full[3 * s]; ddy = d_full[3 * s + 1]; ddz = d_full[3 * s + 2];
+            dc[3 * i] = ddx; dc[3 * i + 1] = ddy; dc[3 * i + 2] = ddz;
+        } else {
+            ddx = dc[3 * i]; ddy = dc[3 * i + 1]; ddz = dc[3 * i + 2];
+        }
+        const double x = r[3 * s] - ddx, y = r[3 * s + 1] - ddy, z = r[3 * s + 2] - ddz;
         rowx[i] = x; rowy[i] = y; rowz[i] = z;
         colsB[i] = make_double4(x, y, z, row_qs[i]);
-        cols_f[mix_slot[s] + 1] = fix_col(x - cx, y - cy, z - cz, inv_grid, row_qs[i]);
         // difference-form mixed kernel: -2 d_j and |d_j|^2 in grid units, from the SAME fp32 values
-        const float dx = (float)(dc[3 * i] * inv_grid), dy = (float)(dc[3 * i + 1] * inv_grid), dz = (float)(dc[3 * i + 2] * inv_grid);
+        const float dx = (float)(ddx * inv_grid), dy = (float)(ddy * inv_grid), dz = (float)(ddz * inv_grid);
         cols_d[i] = make_float4(-2.0f * dx, -2.0f * dy, -2.0f * dz, (float)row_qs[i]);
         cols_d2[i] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     } else {
@@ -105,20 +107,6 @@ __global__ void prepare_shells_kernel(int nd, int nb_pad, const int *__restrict_
         cols_d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         cols_d2[i] = 0.f;
     }
-}
-
-// Thole-screened pair function g(x) = S(u|x|)/|x| and its gradient coefficient
-// (make_Sij, polarization.py:27-31; used at :94-99).  Zero norm -> 0 (polarization.py:33-37).
-__device__ __forceinline__ void thole_g(double x, double y, double z, double u, double &g, double &c) {
-    const double r2 = x * x + y * y + z * z;
-    if (r2 == 0.0) { g = 0.0; c = 0.0; return; }
-    const double rr = sqrt(r2);
-    const double ex = exp(-u * rr);
-    const double S = 1.0 - (1.0 + 0.5 * rr * u) * ex;
-    const double Sp = 0.5 * u * (1.0 + u * rr) * ex;
-    const double ir = 1.0 / rr;
-    g = S * ir;
-    c = (Sp * ir - S * ir * ir) * ir;     // grad g(x) = c * x
 }
 
 template <int BS>
@@ -169,6 +157,17 @@ __device__ __forceinline__ void fold_splits(const double *__restrict__ part, int
     }
 }
 
+// energy vector from the summed partials (inter, intra, self, |g|^2, static); flags: 1 = report the static part
+// (informational, already inside E_INTER), 2 = form the total (single rank), 4 = keep this rank's static sum
+constexpr int kEPutStatic = 1, kETotal = 2, kESaveStatic = 4;
+__device__ __forceinline__ void write_energy_vector(double *__restrict__ e, const double *res, double *__restrict__ e_static, int flags) {
+    if (flags & kESaveStatic) e_static[0] = res[4];
+    e[UPOL_E_INTER] = res[0]; e[UPOL_E_INTRA] = res[1]; e[UPOL_E_SELF] = res[2]; e[UPOL_E_GNORM2] = res[3];
+    e[UPOL_E_STATIC] = (flags & kEPutStatic) ? e_static[0] : res[4];
+    e[6] = 0.0; e[7] = 0.0;
+    e[UPOL_E_UIND] = (flags & kETotal) ? (res[0] + res[1]) + res[2] : 0.0;
+}
+
 // K4b + K2: per Drude row, fold the column-split partials, apply K*qs, add the spring and the
 // intra-molecular Thole pairs, write the gradient row, and emit per-block energy partials.
 __global__ void __launch_bounds__(kFinBlock)
@@ -179,8 +178,10 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
                      const double *__restrict__ row_k,
                      const int *__restrict__ th_ptr, const int *__restrict__ th_row,
                      const double *__restrict__ th_u, double *__restrict__ phi_static,
-                     bool with_grad, double *__restrict__ gc, double *__restrict__ eblock) {
+                     bool with_grad, double *__restrict__ gc, double *__restrict__ eblock,
+                     int *__restrict__ ticket, double *__restrict__ e_out, double *__restrict__ e_static, int e_flags) {
     __shared__ double sm[kFinBlock / 32];
+    __shared__ int is_last;
     __shared__ double fold[kFinLanes][kFinRows][kPartComps];
     const int gw = gate ? *gate : 0;
     if (gw & kGateDone) return;
@@ -244,6 +245,24 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
     if (threadIdx.x == 0) {
         double *o = eblock + kEblockComps * (int64_t)blockIdx.x;
         o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3; o[4] = s4;
+        __threadfence();
+        is_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    // The block that finishes last sums the per-block partials in FIXED order (deterministic, whichever
+    // block that is) and writes the energy vector: no separate reduce / assemble launches, no memset.
+    __threadfence();
+    double res[kEblockComps];
+#pragma unroll
+    for (int c = 0; c < kEblockComps; ++c) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += kFinBlock) v += __ldcg(eblock + (int64_t)b * kEblockComps + c);
+        res[c] = block_sum<kFinBlock>(v, sm);
+    }
+    if (threadIdx.x == 0) {
+        *ticket = 0;
+        write_energy_vector(e_out, res, e_static, e_flags);
     }
 }
 
@@ -284,14 +303,9 @@ __global__ void reduce_blocks_kernel(int nblock, int ncomp, const double *__rest
     }
 }
 
-// energy vector assembly: e[INTER], e[INTRA], e[SELF], e[GNORM2] hold (all-reduced) partial sums
-__global__ void assemble_energy_kernel(double *__restrict__ e, double *__restrict__ e_static,
-                                       bool put_static, bool total, bool save_static = false) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        if (save_static) e_static[0] = e[UPOL_E_STATIC];     // fused pass: this rank's partial, kept with phi_static
-        if (put_static) e[UPOL_E_STATIC] = e_static[0];      // informational; already inside E_INTER
-        if (total) e[UPOL_E_UIND] = (e[UPOL_E_INTER] + e[UPOL_E_INTRA]) + e[UPOL_E_SELF];
-    }
+// after the all-reduce over ranks (sharded runs): total from the summed parts
+__global__ void assemble_energy_kernel(double *__restrict__ e) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) e[UPOL_E_UIND] = (e[UPOL_E_INTER] + e[UPOL_E_INTRA]) + e[UPOL_E_SELF];
 }
 
 __global__ void gather3_kernel(int nd, const int *__restrict__ row_site, const double *__restrict__ full,
@@ -300,6 +314,19 @@ __global__ void gather3_kernel(int nd, const int *__restrict__ row_site, const d
     if (i >= nd) return;
     const int s = row_site[i];
     compact[3 * i] = full[3 * s]; compact[3 * i + 1] = full[3 * s + 1]; compact[3 * i + 2] = full[3 * s + 2];
+}
+
+// gradient rows -> the reference's (nsite,3) layout; sites without a Drude (and rows outside [row_lo, row_hi))
+// get an exact zero, so no memset precedes it
+__global__ void scatter_grad_kernel(int nsite, int row_lo, int row_hi, const int *__restrict__ site_row,
+                                    const double *__restrict__ compact, double *__restrict__ full) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsite) return;
+    const int row = site_row[i];
+    const bool on = row >= row_lo && row < row_hi;
+    full[3 * i] = on ? compact[3 * row] : 0.0;
+    full[3 * i + 1] = on ? compact[3 * row + 1] : 0.0;
+    full[3 * i + 2] = on ? compact[3 * row + 2] : 0.0;
 }
 
 __global__ void scatter3_kernel(int nd, const int *__restrict__ row_site, const double *__restrict__ compact,
@@ -334,6 +361,8 @@ int choose_split(const upol_system *s, int64_t n_rows, int n_tiles, int rows_per
     int64_t sp = (target + rb - 1) / rb;
     sp = std::min<int64_t>(sp, n_tiles);
     sp = std::min<int64_t>(sp, s->max_split);
+    // never more splits than the partial-sum buffer holds for this many rows
+    sp = std::min<int64_t>(sp, (int64_t)(s->part_elems / ((size_t)kPartComps * (size_t)round_up(std::max<int64_t>(n_rows, 1), 512))));
     return (int)std::max<int64_t>(1, sp);
 }
 
@@ -363,7 +392,6 @@ int sys_static_part(upol_system *s, cudaStream_t st) {
     a.n_tiles = a.n_tiles_a;
     a.n_split = choose_split(s, a.n_rows, a.n_tiles, fp64_rows_per_block());
     if (a.n_rows > 0) {
-        // periodic box: same rows and columns, Ewald pair function (ewald.cu) instead of 1/r
         // periodic boxes only (same rows and columns, Ewald pair function, ewald.cu); under open boundaries
         // the static potential is fused into the main fp64 pass (pair_fp64_kernel<FUSE>)
         if (!s->ewald) return UPOL_ERR_ARG;
@@ -381,16 +409,19 @@ int sys_static_part(upol_system *s, cudaStream_t st) {
     return UPOL_OK;
 }
 
+// One evaluation = prepare (shells, shell columns; also gathers d from the (nsite,3) layout when o.d_full is
+// set) -> pair kernel(s) -> finalize (fold, K qs, springs, Thole pairs, gradient rows; its last block sums
+// the energy vector).  Three launches, no memset.
 int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, double *energy_dev,
                      double *gcmp, cudaStream_t st) {
     if (o.precision != UPOL_FP64 && o.precision != UPOL_MIXED) return UPOL_ERR_ARG;
     if (s->ewald && (o.precision != UPOL_FP64 || o.phase_switch)) return UPOL_ERR_ARG;
+    if (o.d_full != nullptr && dcmp != s->dc) return UPOL_ERR_ARG;
     // Mixed mode: ONE fp32 pass in cancellation-free difference form delivers the row potentials with the
     // static part already removed, and the field (pair_diff.cu); no fp64 pair kernel, no static pass.
     // The minimiser (phase_switch) launches both field kernels and lets the gate word pick one.
     const bool mixed = o.precision == UPOL_MIXED;
     const bool diff_energy = mixed && o.want_energy && !o.phase_switch;
-    static const bool old_mixed = getenv("UPOL_OLD_MIXED") != nullptr;      // A/B switch: round-1 field kernel
     // fp64 energies need the static potential of the rows: cached per geometry; formed by the Ewald kernels
     // under a box, and inside the main pass (fused) under open boundaries
     const bool fuse_static = o.want_energy && !diff_energy && !s->static_valid && !s->ewald;
@@ -400,16 +431,15 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
     }
     if (s->nd > 0) {
         prepare_shells_kernel<<<nblk(s->nb_pad, 256), 256, 0, st>>>(
-            (int)s->nd, (int)s->nb_pad, s->row_site, s->r, dcmp, s->row_qs,
-            s->centre[0], s->centre[1], s->centre[2], s->inv_grid, s->mix_slot, s->rowx, s->rowy, s->rowz,
-            s->cols + s->na_pad, s->cols_f, s->cols_d, s->cols_d2);
+            (int)s->nd, (int)s->nb_pad, s->row_site, s->r, o.d_full, const_cast<double *>(dcmp), s->row_qs, s->inv_grid,
+            s->rowx, s->rowy, s->rowz, s->cols + s->na_pad, s->cols_d, s->cols_d2);
     }
     PairArgs a = base_args(s);
     a.rx = s->rowx; a.ry = s->rowy; a.rz = s->rowz;
     a.n_tiles = (int)((s->na_pad + s->nb_pad) / kTileCols);
     a.gate = o.gate;
     double *e = energy_dev ? energy_dev : s->energy;
-    UPOL_CUDA(cudaMemsetAsync(e, 0, UPOL_E_SIZE * sizeof(double), st));
+    const bool reduce = o.reduce_ranks && s->nranks > 1;
     if (a.n_rows > 0) {
         const int split64 = choose_split(s, a.n_rows, a.n_tiles, fp64_rows_per_block());
         int split_pot = 0, split_f64 = 0, split_mx = 0;
@@ -437,52 +467,49 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
             rc = launch_pair_fp64(b, o.want_energy, f64_field, fuse_static, st);
             if (timed) { cudaEventRecord(s->tev[s->tev_used + 1], st); s->tev_used += 2; }
             if (rc) return rc;
+            ++s->launches;
             if (o.want_energy) split_pot = split64;
             if (f64_field) split_f64 = split64;
         }
         if (mx_launch && !s->ewald) {
             PairArgs b = a;
-            const bool use_old = old_mixed && !diff_energy;
-            if (use_old) {
-                b.cols = s->cols_f;                       // one section: core and shell of a site adjacent
-                b.n_tiles = b.n_tiles_a = (int)(s->nm_pad / kTileCols);
-                b.exA_lo = s->exM_lo; b.exA_len = s->exM_len;
-                b.n_split = choose_split(s, a.n_rows, b.n_tiles, kBlock * kRowsMixed);
-            } else {
-                b.cols = s->cols_x; b.cols_d = s->cols_d; b.cols_d2 = s->cols_d2; b.dcomp = dcmp;
-                b.n_tiles_a = (int)(s->nb_pad / kTileCols);
-                b.n_tiles = (int)((s->nb_pad + s->nn_pad) / kTileCols);
-                b.exA_lo = s->exP_lo; b.exA_len = s->exP_len; b.exB_lo = s->exN_lo; b.exB_len = s->exN_len;
-                b.n_split = choose_split(s, a.n_rows, b.n_tiles, diff_rows_per_block(diff_energy));
-            }
+            b.cols = s->cols_x; b.cols_d = s->cols_d; b.cols_d2 = s->cols_d2; b.dcomp = dcmp;
+            b.n_tiles_a = (int)(s->nb_pad / kTileCols);
+            b.n_tiles = (int)((s->nb_pad + s->nn_pad) / kTileCols);
+            b.exA_lo = s->exP_lo; b.exA_len = s->exP_len; b.exB_lo = s->exN_lo; b.exB_len = s->exN_len;
+            b.n_split = choose_split(s, a.n_rows, b.n_tiles, diff_rows_per_block(diff_energy));
             b.gate_skip_mask = kGateDone | (o.phase_switch ? kGatePhase64 : 0);
             const bool timed = s->timing && !f64_launch && s->tev_used + 2 <= (int)s->tev.size();
             if (timed) cudaEventRecord(s->tev[s->tev_used], st);
-            rc = use_old ? launch_pair_mixed(b, st) : launch_pair_diff(b, diff_energy, st);
+            rc = launch_pair_diff(b, diff_energy, st);
             if (timed) { cudaEventRecord(s->tev[s->tev_used + 1], st); s->tev_used += 2; }
             if (rc) return rc;
+            ++s->launches;
             split_mx = b.n_split;
             if (!o.phase_switch) split_f64 = b.n_split;   // no gate: the mixed partials are THE field
             if (diff_energy) split_pot = b.n_split;
         }
         const int nb = (int)nblk(a.n_rows, kFinRows);
+        const int e_flags = ((o.want_energy && !diff_energy && !fuse_static) ? kEPutStatic : 0) | (reduce ? 0 : kETotal) |
+                            (fuse_static ? kESaveStatic : 0);
         finalize_rows_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, split_pot, split_f64, split_mx, fuse_static ? 1 : 0,
                                                        o.gate, o.phase_switch ? 1 : 0, s->part, a.part_stride,
                                                        s->row_site, s->r, dcmp, s->row_qs, s->row_k,
                                                        s->th_ptr, s->th_row, s->th_u,
-                                                       (o.want_energy && !diff_energy) ? s->phi_static : nullptr, o.want_grad, gcmp, s->eblock);
-        // eblock comps (inter, intra, self, g2, static) -> energy[INTER..STATIC], contiguous by design
-        reduce_blocks_kernel<<<1, 256, 0, st>>>(nb, kEblockComps, s->eblock, e + UPOL_E_INTER, 1);
+                                                       (o.want_energy && !diff_energy) ? s->phi_static : nullptr, o.want_grad, gcmp,
+                                                       s->eblock, s->ticket, e, s->e_static, e_flags);
         UPOL_CUDA(cudaGetLastError());
+        s->launches += 2 + (s->nd > 0 ? 0 : -1);
+        if (fuse_static) s->static_valid = true;
+    } else {
+        // a rank without rows contributes zeros (and its cached static sum, which is zero as well)
+        UPOL_CUDA(cudaMemsetAsync(e, 0, UPOL_E_SIZE * sizeof(double), st));
     }
-    // static partial of this rank's rows, then (sharded runs) one all-reduce of the vector
-    const bool reduce = o.reduce_ranks && s->nranks > 1;
-    assemble_energy_kernel<<<1, 32, 0, st>>>(e, s->e_static, o.want_energy && !diff_energy, !reduce, fuse_static);
-    if (fuse_static) s->static_valid = true;
     if (reduce) {
         int rc = comm_allreduce_sum(s, e, UPOL_E_SIZE, st);
         if (rc) return rc;
-        assemble_energy_kernel<<<1, 32, 0, st>>>(e, s->e_static, false, true);
+        assemble_energy_kernel<<<1, 32, 0, st>>>(e);
+        ++s->launches;
     }
     UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
@@ -496,13 +523,10 @@ int sys_gather_d(upol_system *s, const double *d_full, double *d_compact, cudaSt
 }
 
 int sys_scatter_g(upol_system *s, const double *g_compact, double *g_full, cudaStream_t st) {
-    // non-polarisable sites: gradient exactly zero
-    UPOL_CUDA(cudaMemsetAsync(g_full, 0, sizeof(double) * 3 * s->nsite, st));
-    if (s->nd == 0) return UPOL_OK;
-    const int64_t n = s->nranks > 1 ? s->nd : (s->row_hi - s->row_lo);
-    const int64_t r0 = s->nranks > 1 ? 0 : s->row_lo;
-    if (n > 0)
-        scatter3_kernel<<<nblk(n, 256), 256, 0, st>>>((int)n, s->row_site + r0, g_compact + 3 * r0, g_full);
+    // after the all-gather of a sharded run every row is present; a single rank shows its row range only
+    const int64_t lo = s->nranks > 1 ? 0 : s->row_lo, hi = s->nranks > 1 ? s->nd : s->row_hi;
+    scatter_grad_kernel<<<nblk(s->nsite, 256), 256, 0, st>>>((int)s->nsite, (int)lo, (int)hi, s->site_row, g_compact, g_full);
+    ++s->launches;
     UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
 }
@@ -579,9 +603,8 @@ int sys_box_from_device(upol_system *s, cudaStream_t st) {
 int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream_t st) {
     // r is already in s->r (device); (re)build the d-independent columns with the current box
     (void)r_dev_or_null;
-    build_core_columns_kernel<<<nblk(std::max(s->na_pad, s->nm_pad), 256), 256, 0, st>>>(
-        (int)s->nsite, (int)s->na_pad, s->r, s->qc, s->qs, s->centre[0], s->centre[1], s->centre[2], s->inv_grid,
-        s->mix_slot, (int)(s->nsite + s->nd), (int)s->nm_pad, s->cols, s->cols_f, s->cols_static, s->col_qeff);
+    build_core_columns_kernel<<<nblk(s->na_pad, 256), 256, 0, st>>>(
+        (int)s->nsite, (int)s->na_pad, s->r, s->qc, s->qs, s->cols, s->cols_static, s->col_qeff);
     build_diff_columns_kernel<<<nblk(std::max<int64_t>(s->nsite, std::max(s->nb_pad, s->nn_pad)), 256), 256, 0, st>>>(
         (int)s->nsite, (int)s->nd, (int)s->nb_pad, (int)s->nn_pad, s->r, s->qc, s->site_row, s->site_nslot,
         s->centre[0], s->centre[1], s->centre[2], s->inv_grid, s->cols_x);
@@ -589,8 +612,25 @@ int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream
         build_static_rows_kernel<<<nblk(s->nd, 256), 256, 0, st>>>((int)s->nd, s->row_site, s->r,
                                                                     s->srowx, s->srowy, s->srowz);
     UPOL_CUDA(cudaGetLastError());
+    s->launches += 2 + (s->nd > 0 ? 1 : 0);
     s->static_valid = false;
     ewald_invalidate(s);
+    return UPOL_OK;
+}
+
+// Uself = 1/2 sum k |d|^2 (polarization.py:44-48) on plain arrays; one block, fixed summation order
+__global__ void uself_kernel(int64_t n, const double *__restrict__ d, const double *__restrict__ k, double *__restrict__ out) {
+    __shared__ double sm[256 / 32];
+    double v = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 256)
+        v += 0.5 * k[i] * (d[3 * i] * d[3 * i] + d[3 * i + 1] * d[3 * i + 1] + d[3 * i + 2] * d[3 * i + 2]);
+    const double t = block_sum<256>(v, sm);
+    if (threadIdx.x == 0) out[0] = t;
+}
+
+int sys_uself(const double *d, const double *k, int64_t n, double *out, cudaStream_t st) {
+    uself_kernel<<<1, 256, 0, st>>>(n, d, k, out);
+    UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
 }
 
@@ -639,19 +679,27 @@ finalize_sites_kernel(int nsite, int n_split, const double *__restrict__ part, i
 int sys_coulomb_static(upol_system *s, double *out2, cudaStream_t st) {
     // scratch: rows (3*nsite doubles), site exclusion intervals, columns, partials
     const int64_t n = s->nsite;
-    double *rows = nullptr, *part = nullptr, *eblock = nullptr;
-    int *ex = nullptr;
-    double4 *cols = nullptr;
+    // scratch freed on every exit path (a CUDA error on the way must not leak it: Ucoul / Ucoul_static call
+    // this once per evaluation)
+    struct Scratch {
+        double *rows = nullptr, *part = nullptr, *eblock = nullptr;
+        int *ex = nullptr;
+        double4 *cols = nullptr;
+        ~Scratch() { cudaFree(rows); cudaFree(part); cudaFree(eblock); cudaFree(ex); cudaFree(cols); }
+    } sc;
     const int ntile = (int)(s->na_pad / kTileCols);
     const int64_t rb = (n + kRowTile - 1) / kRowTile;
     int split = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (148 * 8 + rb - 1) / rb));
     const int64_t stride = part_stride_for(n);
     const int nb = (int)nblk(n, kFinRows);
-    UPOL_CUDA(cudaMalloc((void **)&rows, sizeof(double) * 3 * n));
-    UPOL_CUDA(cudaMalloc((void **)&ex, sizeof(int) * 4 * n));
-    UPOL_CUDA(cudaMalloc((void **)&cols, sizeof(double4) * s->na_pad));
-    UPOL_CUDA(cudaMalloc((void **)&part, sizeof(double) * split * kPartComps * stride));
-    UPOL_CUDA(cudaMalloc((void **)&eblock, sizeof(double) * nb));
+    UPOL_CUDA(cudaMalloc((void **)&sc.rows, sizeof(double) * 3 * n));
+    UPOL_CUDA(cudaMalloc((void **)&sc.ex, sizeof(int) * 4 * n));
+    UPOL_CUDA(cudaMalloc((void **)&sc.cols, sizeof(double4) * s->na_pad));
+    UPOL_CUDA(cudaMalloc((void **)&sc.part, sizeof(double) * split * kPartComps * stride));
+    UPOL_CUDA(cudaMalloc((void **)&sc.eblock, sizeof(double) * nb));
+    double *rows = sc.rows, *part = sc.part, *eblock = sc.eblock;
+    int *ex = sc.ex;
+    double4 *cols = sc.cols;
     std::vector<int> hex(4 * n, 0);
     for (int64_t i = 0; i < n; ++i) {
         const int m = s->h_mol[i];
@@ -675,7 +723,6 @@ int sys_coulomb_static(upol_system *s, double *out2, cudaStream_t st) {
     }
     UPOL_CUDA(cudaGetLastError());
     UPOL_CUDA(cudaStreamSynchronize(st));   // hex (host vector) and the scratch die here
-    cudaFree(rows); cudaFree(ex); cudaFree(cols); cudaFree(part); cudaFree(eblock);
     return UPOL_OK;
 }
 
@@ -770,6 +817,9 @@ int sys_core_forces(upol_system *s, const double *dcmp, double *dudr, cudaStream
         }
         UPOL_CUDA(cudaMemcpy(s->exS_lo, ex.data(), sizeof(int) * ex.size(), cudaMemcpyHostToDevice));
         UPOL_CUDA(cudaMemset(s->site_x, 0, sizeof(double) * 3 * s->ns_pad));
+        // the copies above ran on the legacy stream from pageable memory; `st` may be a non-blocking stream
+        // that is not ordered against it, so the tables must have landed before anything is enqueued on `st`
+        UPOL_CUDA(cudaDeviceSynchronize());
     }
     UPOL_CUDA(cudaMemsetAsync(dudr, 0, sizeof(double) * 3 * n, st));
     if (nd == 0) return UPOL_OK;
@@ -780,8 +830,8 @@ int sys_core_forces(upol_system *s, const double *dcmp, double *dudr, cudaStream
     const int64_t ns = s_hi - s_lo;
     double *F = s->cf_tmp, *H = F + 3 * nd, *GH = H + 3 * nd;
     prepare_shells_kernel<<<nblk(s->nb_pad, 256), 256, 0, st>>>(
-        (int)nd, (int)s->nb_pad, s->row_site, s->r, dcmp, s->row_qs, s->centre[0], s->centre[1], s->centre[2],
-        s->inv_grid, s->mix_slot, s->rowx, s->rowy, s->rowz, s->cols + s->na_pad, s->cols_f, s->cols_d, s->cols_d2);
+        (int)nd, (int)s->nb_pad, s->row_site, s->r, nullptr, const_cast<double *>(dcmp), s->row_qs, s->inv_grid,
+        s->rowx, s->rowy, s->rowz, s->cols + s->na_pad, s->cols_d, s->cols_d2);
     build_force_tables_kernel<<<nblk(std::max<int64_t>(n, s->nb_pad), 256), 256, 0, st>>>(
         (int)n, (int)nd, (int)s->nb_pad, s->r, s->row_site, s->row_qs, s->site_x, s->site_y, s->site_z, s->cols_dcore);
     if (s->ewald) {

@@ -129,7 +129,8 @@ class UindSystem:
     # -- hot path -------------------------------------------------------------------------
     def energy_grad(self, d, precision="fp64", want_grad=True, want_energy=True):
         """(energy vector [8] on device or None, grad (N,3) on device or None).  Asynchronous.
-        ``precision`` is the arithmetic of the gradient; energies are always fp64."""
+        ``precision`` = "fp64" or "mixed" (fp32 pair arithmetic in cancellation-free difference form with fp64
+        accumulation, for the energy and the gradient alike; 1e-5 relative)."""
         prec = {"fp64": L.FP64, "mixed": L.MIXED}[precision]
         with torch.cuda.device(self.device):
             dd = self._dev_f64(d, 3 * self.nsite)
@@ -169,9 +170,12 @@ class UindSystem:
             L.check(L.lib().upol_coulomb_static_dev(self._h, out.data_ptr(), self._stream()))
         return out
 
-    def minimize(self, d0=None, tol=1e-4, maxiter=500, method="lbfgs", precision="fp64", history=8, check_every=4):
+    def minimize(self, d0=None, tol=1e-4, maxiter=500, method="lbfgs", precision="fp64", history=8, check_every=4,
+                 strict=False):
         """Minimise U_ind over the Drude displacements on the device.
-        Returns (d_opt (N,3) device tensor, result dict)."""
+        Returns (d_opt (N,3) device tensor, result dict).  A lost peer (UPOL_FLAG_COMM) always raises; with
+        ``strict`` a non-finite gradient raises too and an unconverged run warns (what ``drudeOpt`` does) -
+        otherwise those flags are only reported in ``info['flags']``."""
         with torch.cuda.device(self.device):
             d = torch.zeros(3 * self.nsite, dtype=torch.float64, device=self.device) if d0 is None \
                 else self._dev_f64(d0, 3 * self.nsite).clone()
@@ -186,6 +190,10 @@ class UindSystem:
                          "upol_minimize_dev")
         info = {"energy": np.array(res.energy[:]), "U_ind": res.energy[L.E_UIND], "gnorm": res.gnorm,
                 "iterations": res.iterations, "evaluations": res.evaluations, "flags": res.flags, "status": rc}
+        if strict:
+            L.check_min_flags(res.flags, "UindSystem.minimize")
+        elif res.flags & L.FLAG_COMM:
+            raise L.UpolError("UindSystem.minimize: a peer rank did not deliver within the time-out (UPOL_FLAG_COMM)")
         return d.reshape(self.nsite, 3), info
 
     def invalidate_static(self):
@@ -198,6 +206,10 @@ class UindSystem:
 
     def set_kernel_timing(self, enable=True):
         L.check(L.lib().upol_system_set_kernel_timing(self._h, int(enable)))
+
+    def launch_count(self):
+        """Kernels of the library launched for this system so far."""
+        return int(L.lib().upol_system_launch_count(self._h))
 
     def kernel_time(self):
         """(summed ms, launches) of the main pair kernel since the last call."""

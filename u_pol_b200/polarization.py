@@ -70,9 +70,36 @@ def _compact(Rij, Qi_shell, Qi_core, u_scale, k=None):
     return r_core, qc, qs, kk, th
 
 
+# The reference's main() calls drudeOpt and then Uind on the SAME dense inputs (polarization.py:246-257).  Building
+# a device system (allocations, uploads) per call would dominate for the small systems that CLI runs, so the
+# most recently used systems stay resident, keyed by a digest of the compact inputs and the device.
+_CACHE = {}
+_CACHE_MAX = 2
+
+
 def _system(Rij, Qi_shell, Qi_core, u_scale, k=None):
+    import hashlib
+
     r_core, qc, qs, kk, th = _compact(Rij, Qi_shell, Qi_core, u_scale, k)
-    return UindSystem.from_compact(r_core, qc, qs, kk, th), r_core.shape[0], r_core.shape[1]
+    h = hashlib.blake2b(digest_size=16)
+    for a in (r_core, qc, qs, kk, th if th is not None else np.zeros(0)):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        h.update(str(a.shape).encode())
+        h.update(a.tobytes())
+    key = (h.hexdigest(), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    sys_ = _CACHE.pop(key, None)
+    if sys_ is None or getattr(sys_, "_h", None) is None:
+        sys_ = UindSystem.from_compact(r_core, qc, qs, kk, th)
+    _CACHE[key] = sys_                              # most recently used last
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.pop(next(iter(_CACHE))).close()
+    return sys_, r_core.shape[0], r_core.shape[1]
+
+
+def clear_cache():
+    """Release the device systems kept by the dense wrappers."""
+    while _CACHE:
+        _CACHE.popitem()[1].close()
 
 
 def _dij(Dij, nmol, natoms):
@@ -104,26 +131,24 @@ def make_Sij(Rij, u_scale):
 
 
 def Uself(Dij, k):
-    """1/2 sum k |d|^2 (polarization.py:44-48) - the UPOL_E_SELF component of the device pass."""
-    kk = _np64(k)
-    nmol, natoms = kk.shape
-    # a system of isolated sites: q_core = 0, q_shell = 1 wherever k != 0, far apart molecules
-    # are not needed - the self term does not depend on geometry
-    r = np.zeros((nmol, natoms, 3))
-    r[..., 0] = np.arange(nmol * natoms).reshape(nmol, natoms)
-    sys_ = UindSystem.from_compact(r, np.zeros((nmol, natoms)), (kk != 0).astype(np.float64), kk, None)
-    e, _ = sys_.energy_grad(_dij(Dij, nmol, natoms), want_grad=False)
-    out = e[L.E_SELF].clone()
-    sys_.close()
+    """1/2 sum k |d|^2 (polarization.py:44-48), summed on the device in a fixed order."""
+    import ctypes as C
+
+    if not torch.cuda.is_available():
+        raise L.UpolError("u_pol_b200 needs a CUDA device")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    kk = torch.as_tensor(_np64(k)).reshape(-1).to(dev).contiguous()
+    d = _dij(Dij, kk.numel(), 1).to(torch.float64).to(dev).contiguous()
+    out = torch.empty((), dtype=torch.float64, device=dev)
+    L.check(L.lib().upol_uself_dev(d.data_ptr(), kk.data_ptr(), kk.numel(), out.data_ptr(),
+                                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "upol_uself_dev")
     return out
 
 
 def Ucoul_static(Rij, Qi_shell, Qj_shell, Qi_core, Qj_core):
     """polarization.py:50-61."""
     sys_, _, _ = _system(Rij, Qi_shell, Qi_core, 0.0)
-    out = sys_.coulomb_static()[1].clone()
-    sys_.close()
-    return out
+    return sys_.coulomb_static()[1].clone()
 
 
 def Ucoul(Rij, Dij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale):
@@ -131,18 +156,14 @@ def Ucoul(Rij, Dij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale):
     sys_, nmol, natoms = _system(Rij, Qi_shell, Qi_core, u_scale)
     e, _ = sys_.energy_grad(_dij(Dij, nmol, natoms), want_grad=False)
     stat = sys_.coulomb_static()
-    out = (e[L.E_INTER] + e[L.E_INTRA]) + stat[1]
-    sys_.close()
-    return out
+    return (e[L.E_INTER] + e[L.E_INTRA]) + stat[1]
 
 
 def Uind(Rij, Dij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k):
     """polarization.py:111-151 - total induction energy, 0-d fp64 tensor on the device."""
     sys_, nmol, natoms = _system(Rij, Qi_shell, Qi_core, u_scale, k)
     e, _ = sys_.energy_grad(_dij(Dij, nmol, natoms), want_grad=False)
-    out = e[L.E_UIND].clone()
-    sys_.close()
-    return out
+    return e[L.E_UIND].clone()
 
 
 def Uind_and_grad(Rij, Dij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k, precision="fp64"):
@@ -151,9 +172,7 @@ def Uind_and_grad(Rij, Dij, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k, pr
     sys_, nmol, natoms = _system(Rij, Qi_shell, Qi_core, u_scale, k)
     e, g = sys_.energy_grad(_dij(Dij, nmol, natoms), precision=precision)
     shape = tuple(Dij.shape) if hasattr(Dij, "shape") else (nmol * natoms * 3,)
-    out = (e[L.E_UIND].clone(), g.reshape(shape))
-    sys_.close()
-    return out
+    return e[L.E_UIND].clone(), g.reshape(shape)
 
 
 def drudeOpt(Rij, Dij0, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k, methods=["BFGS"], d_ref=None,
@@ -168,7 +187,9 @@ def drudeOpt(Rij, Dij0, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k, method
     d_opt = None
     for method in methods:
         m = {"BFGS": "lbfgs", "LBFGS": "lbfgs", "L-BFGS": "lbfgs", "CG": "cg"}.get(str(method).upper(), "lbfgs")
-        d_opt, info = sys_.minimize(_dij(Dij0, nmol, natoms), tol=tol, maxiter=maxiter, method=m, precision=precision)
+        # strict: a non-finite gradient or a lost peer raises, an unconverged run warns - never a silent bad d_opt
+        d_opt, info = sys_.minimize(_dij(Dij0, nmol, natoms), tol=tol, maxiter=maxiter, method=m, precision=precision,
+                                    strict=True)
         logger.info("U_POL_B200.%s: %d iterations, %d evaluations, |g| = %.3e",
                     m.upper(), info["iterations"], info["evaluations"], info["gnorm"])
         if d_ref is not None:
@@ -177,6 +198,5 @@ def drudeOpt(Rij, Dij0, Qi_shell, Qj_shell, Qi_core, Qj_core, u_scale, k, method
                     _ = torch.linalg.norm(torch.as_tensor(_np64(d_ref)).reshape(-1).to(d_opt.device) - d_opt.reshape(-1))
             except AttributeError:
                 pass
-    sys_.close()
     shape = tuple(Dij0.shape) if hasattr(Dij0, "shape") else (nmol * natoms * 3,)
     return d_opt.reshape(shape)

@@ -83,6 +83,7 @@ def run_scan(indir, monomer, outfile="induction_data.csv", tol=1e-4, positions="
     ``monomer``: dict with ``q_core, q_shell, alpha, thole_u`` for ONE molecule (as in
     ``u_pol_b200/data/monomers.json``); every conformer is nmol = natoms_total / natoms molecules of it.
     Returns (dimer_ids, sapt_induction, md_induction) arrays in file order."""
+    from . import _lib as L
     from .engine import batched_minimize
     from .topology import ONE_4PI_EPS0
 
@@ -108,8 +109,19 @@ def run_scan(indir, monomer, outfile="induction_data.csv", tol=1e-4, positions="
     qc, qs, al = tile(monomer["q_core"]), tile(monomer["q_shell"]), tile(monomer["alpha"])
     k = np.where(al == 0, 0.0, ONE_4PI_EPS0 * qs**2 / np.where(al == 0, 1.0, al))
     _, e, _ = batched_minimize(r, qc, qs, k, tile(monomer["thole_u"]), tol=tol, device=device)
-    md = e[:, 0].cpu().numpy()
+    e = e.cpu().numpy()
+    md = e[:, 0].copy()
     ids, sapt = np.array(ids), np.array(sapt)
+    # per-system UPOL_FLAG_* bits (column 6): a minimisation that went non-finite or did not converge must not
+    # become a plausible-looking CSV row - it is written as nan and counted
+    flags = e[:, 6].astype(np.int64)
+    bad = (flags & (L.FLAG_NONFINITE | L.FLAG_NOT_CONVERGED)) != 0
+    if bad.any():
+        import warnings
+
+        md[bad] = np.nan
+        warnings.warn(f"run_scan: {int(bad.sum())} of {len(md)} dimers did not minimise cleanly "
+                      f"(ids {ids[bad][:10].tolist()}{'...' if bad.sum() > 10 else ''}); written as nan", RuntimeWarning)
     if outfile:
         np.savetxt(outfile, np.column_stack([sapt, md, ids]), delimiter=",",
                    header="SAPT_Induction,MD_Induction,DimerID", comments="")     # wrapper.py:367-373
