@@ -2,23 +2,29 @@
 """Benchmark of the U_ind hot path (BASELINE.json: "U_ind energy+grad pair-interactions/s and
 minimise wall-time at N=100k Drudes").
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # reference algorithm on host cores
+    python bench.py --gpus N --steps K --warmup W                     # this repo's CUDA path, config 4
+    python bench.py --config {2,3,4,5} ...                            # the other BASELINE configs
+    python bench.py --impl reference --gpus N --steps K --warmup W    # reference algorithm on host cores
 
-Workload (BASELINE configs[3], SURVEY 8d "config 4"): synthetic imidazole-parameter polarisable
-liquid, 20 000 molecules -> N = 180 000 sites, N_D = 100 000 Drudes, seed 4, d ~ N(0, 0.002 nm)
-on Drude sites.  It fits one GPU, so it is the N=1 workload too; at N>1 the Drude rows are
-sharded by molecule blocks (all columns replicated) and the total work is fixed ("strong").
+Configs (BASELINE.json `configs`):
+  4 (default, the metric's own configuration): synthetic imidazole-parameter polarisable liquid, 20 000
+    molecules -> N = 180 000 sites, N_D = 100 000 Drudes, seed 4, d ~ N(0, 0.002 nm) on Drude sites.  It fits
+    one GPU, so it is the N=1 workload too; at N>1 the Drude rows are sharded by molecule blocks (all columns
+    replicated) and the total work is fixed ("strong").  A step = one full fp64 U_ind + dU/dd evaluation as the
+    reference's jitted value_and_grad does it: d-independent static part RECOMPUTED every step (fused into
+    the main pass), core/shell pass, Thole intra pass, springs, reductions, and (N>1) the exchange of the
+    energy vector and the gradient rows.  value = reference site-pairs per second, P = N(N-1) ordered site
+    pairs per evaluation (the unit in which the JAX/CPU path and the CUDA path are comparable).
+    The same line carries `mixed_step` (the same step in UPOL_MIXED: one fp32 difference-form pass),
+    `minimise` (wall time of the full minimisation, fp64 and mixed) and, at every N, `parity` against values
+    committed from an N=1 run (tests/golden/bench_parity_config4.json).
+  2: SWM4-NDP-style water box, 3 000 molecules (N = 12 000, N_D = 3 000): single full E+grad, same metric.
+  3: imidazole-parameter liquid, 4 000 molecules (N_D = 20 000): full minimisation, metric = wall seconds.
+  5: 10 000 imidazole dimers minimised in one launch (the 312 reference geometries + rigid-body
+     perturbations): systems/s; the 312 originals are checked against the reference's own CSV in-run.
 
-A step = one full U_ind + dU/dd evaluation as the reference's jitted value_and_grad does it:
-the d-independent static part (U_coul_static and the f(R) terms) is RECOMPUTED every step, the
-main core/shell pass, the Thole intra pass, the spring term, the reductions, and (N>1) the
-all-reduce of the energy vector and the all-gather of the gradient rows.
-metric/value = reference site-pairs per second, P = N(N-1) ordered site pairs per evaluation
-(the unit in which the JAX/CPU path and the CUDA path are comparable).
-
-JSON line: see README/DESIGN.md; `roofline.bound` is "fp64" because this path is bound by the
-FP64 pipe (north star), whose peak is measured on the box by an FMA-chain microbenchmark
+JSON line: README/DESIGN.md section 10; `roofline.bound` names the pipe that bounds the kernel (fp64 / fp32
+register-operand bandwidth), whose peak is measured on the box by an FMA-chain microbenchmark
 (MEASURED_PEAKS.json has only HBM and bf16-GEMM peaks).
 """
 from __future__ import annotations
@@ -43,31 +49,39 @@ UNIT = "site-pairs/s"
 WORKLOAD = f"imidazole_liquid_{NMOL}mol_N{9 * NMOL}_ND{5 * NMOL}_seed{SEED}"
 FLOP_PER_INTERACTION = 20
 FLOP_PER_STATIC_INTERACTION = 12
+PARITY_FILE = os.path.join(ROOT, "tests", "golden", "bench_parity_config4.json")
+
+
+def _box(kind, nmol, seed):
+    """Synthetic box, cached under TMPDIR (the 20 000-molecule placement takes ~10 s)."""
+    from u_pol_b200 import synth
+    from u_pol_b200.topology import DrudeSystem
+
+    name = f"{kind}_{nmol}_{seed}"
+    cache = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"upol_bench_{name}.npz")
+    if os.path.isfile(cache):
+        try:
+            z = np.load(cache)
+            m = synth.load_monomer(kind)
+            tile = lambda v: np.ascontiguousarray(np.broadcast_to(v, (nmol,) + v.shape))
+            return DrudeSystem(r_core=z["r"], q_core=tile(m["q_core"]), q_shell=tile(m["q_shell"]),
+                               alpha=tile(m["alpha"]), thole_u=tile(m["thole_u"]), site_names=list(m["site_names"]))
+        except Exception:
+            pass
+    s = synth.imidazole_box(nmol, seed=seed) if kind == "imidazole" else synth.water_box(nmol, seed=seed)
+    try:
+        tmp = cache + f".{os.getpid()}.tmp.npz"
+        np.savez(tmp, r=s.r_core)
+        os.replace(tmp, cache)
+    except Exception:
+        pass
+    return s
 
 
 def make_workload():
     from u_pol_b200 import synth
 
-    cache = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"upol_bench_{WORKLOAD}.npz")
-    s = None
-    if os.path.isfile(cache):
-        try:
-            z = np.load(cache)
-            m = synth.load_monomer("imidazole")
-            tile = lambda v: np.ascontiguousarray(np.broadcast_to(v, (NMOL,) + v.shape))
-            from u_pol_b200.topology import DrudeSystem
-            s = DrudeSystem(r_core=z["r"], q_core=tile(m["q_core"]), q_shell=tile(m["q_shell"]),
-                            alpha=tile(m["alpha"]), thole_u=tile(m["thole_u"]), site_names=list(m["site_names"]))
-        except Exception:
-            s = None
-    if s is None:
-        s = synth.imidazole_box(NMOL, seed=SEED)
-        try:
-            tmp = cache + f".{os.getpid()}.tmp.npz"
-            np.savez(tmp, r=s.r_core)
-            os.replace(tmp, cache)
-        except Exception:
-            pass
+    s = _box("imidazole", NMOL, SEED)
     d = synth.random_displacements(s, seed=SEED + 1, sigma=0.002)
     return s, d
 
@@ -133,12 +147,12 @@ class ClockSampler:
 
 def cpu_sample(s, d, target_seconds):
     """Time the C restatement of the reference on the host cores for a bounded row sample.
-    Returns (site_pairs_per_s, cores, description)."""
+    Returns (site_pairs_per_s, cores, rows, seconds)."""
     from oracle import c_oracle
 
     c_oracle.use_all_cores()
     n = s.nmol * s.natoms
-    rows = 64 * s.natoms
+    rows = min(n, 64 * s.natoms)
     t0 = time.perf_counter()
     c_oracle.energy_grad(s.r_core, d, s.q_core, s.q_shell, s.k, s.thole_u, row_lo=0, row_hi=rows)
     t_probe = max(time.perf_counter() - t0, 1e-4)
@@ -150,6 +164,22 @@ def cpu_sample(s, d, target_seconds):
     return rows * (n - 1) / dt, c_oracle.max_threads(), rows, dt
 
 
+def _config_workload(config):
+    """(system, displacements, workload name) of an energy/gradient or minimisation config."""
+    from u_pol_b200 import synth
+
+    if config == 4:
+        s, d = make_workload()
+        return s, d, WORKLOAD
+    if config == 2:
+        s = _box("water", 3000, 2)
+        return s, synth.random_displacements(s, seed=1, sigma=0.002), "swm4ndp_water_3000mol_N12000_ND3000_seed2"
+    if config == 3:
+        s = _box("imidazole", 4000, 3)
+        return s, synth.random_displacements(s, seed=4, sigma=0.002), "imidazole_liquid_4000mol_N36000_ND20000_seed3"
+    raise SystemExit(f"unknown config {config}")
+
+
 def run_reference(args):
     """Reference arm: the reference's algorithm (C restatement of polarization.py, oracle/uind_oracle.c)
     on all host threads; JAX/jaxopt are not installable in this image."""
@@ -159,10 +189,12 @@ def run_reference(args):
     from oracle import c_oracle
 
     c_oracle.use_all_cores()          # torchrun exports OMP_NUM_THREADS=1 to its workers
-    s, d = make_workload()
+    if args.config == 5:
+        return run_reference_batched(args)
+    s, d, workload = _config_workload(args.config)
     n = s.nmol * s.natoms
     # size one step to ~2 s of host work
-    rows = 64 * s.natoms
+    rows = min(n, 64 * s.natoms)
     t0 = time.perf_counter()
     c_oracle.energy_grad(s.r_core, d, s.q_core, s.q_shell, s.k, s.thole_u, row_lo=0, row_hi=rows)
     t_probe = max(time.perf_counter() - t0, 1e-4)
@@ -174,101 +206,129 @@ def run_reference(args):
     for _ in range(args.steps):
         c_oracle.energy_grad(s.r_core, d, s.q_core, s.q_shell, s.k, s.thole_u, row_lo=0, row_hi=rows)
     dt = (time.perf_counter() - t0) / args.steps
-    value = rows * (n - 1) / dt
+    rate = rows * (n - 1) / dt
     cores = c_oracle.max_threads()
     sample = f"{rows} of {n} site rows x all {n} columns per step (E + dE/dd), oracle/uind_oracle.c, OpenMP"
+    metric, unit, value, hib = METRIC, UNIT, rate, True
+    if args.config == 3:
+        # minimisation = evaluations x time of one evaluation; the evaluation count is that of the device
+        # minimiser on this workload (16 at tol 1e-4, profiles/r02_config_table.txt) - an extrapolation, stated
+        evals = 16
+        metric, unit, hib = "uind_minimise_wall_s", "s", False
+        value = evals * n * (n - 1) / rate
+        sample += f"; minimise = {evals} evaluations x (full-evaluation time extrapolated from the row sample)"
     out = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": hib,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sites": n, "drudes": int((s.q_shell != 0).sum()),
+        "config": {"workload": workload, "sites": n, "drudes": int((s.q_shell != 0).sum()),
                    "note": "reference algorithm restated in C (JAX/jaxopt/OpenMM not installable here); "
                            "each step is a bounded row sample of the workload"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
 
 
-def run_cuda(args):
-    import torch
-    import torch.distributed as dist
+def _dimer_batch(nbatch):
+    from u_pol_b200 import synth
 
-    from u_pol_b200 import _lib as L
-    from u_pol_b200.engine import UindSystem, measure_fma_peak
+    z = np.load(os.path.join(ROOT, "tests", "golden", "dimers312.npz"))
+    al, qs = z["alpha"], z["q_shell"]
+    k = np.where(al == 0, 0.0, 138.93545764438198 * qs**2 / np.where(al == 0, 1.0, al))
+    r = synth.perturbed_dimers(z["r_core"], nbatch, seed=5)
+    return z, r, k
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
 
-    s, d_host = make_workload()
-    n = s.nmol * s.natoms
-    nd = int((s.q_shell != 0).sum())
-    sysm = UindSystem.from_drude_system(s, device=local_rank)
-    exchange = "none"
-    if world > 1:
-        sysm.attach_process_group()
-        exchange = "peer-memory stores (CUDA IPC/NVLink) fused into the update kernel" if getattr(sysm, "p2p", False) else "nccl"
-    d_dev = torch.as_tensor(d_host.reshape(-1)).to(dev)
-    pairs_per_step = n * (n - 1)
-    inter_local = sysm.interactions(False)
-    inter_static_local = sysm.interactions(True)
-    n_d_mol = int((s.q_shell[0] != 0).sum())
-    inter_total = s.nmol * n_d_mol * ((n - s.natoms) + (nd - n_d_mol))          # I_inter, SURVEY 8d
-    inter_static_total = s.nmol * n_d_mol * (n - s.natoms)
+def run_reference_batched(args):
+    """Config 5 on the host: the dense restatement (oracle/uind_dense.py, SciPy BFGS standing in for jaxopt)
+    minimises a bounded sample of the dimers, one after the other as wrapper.py's loop does."""
+    from oracle import uind_dense
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    z, r, k = _dimer_batch(10000)
+    nsample = 16
+    t0 = time.perf_counter()
+    for b in range(nsample):
+        R, qis, qjs, qic, qjc, u, kk = uind_dense.dense_inputs(r[b], z["q_core"], z["q_shell"], k, z["thole_u"])
+        uind_dense.minimise(R, np.zeros_like(r[b]), qis, qjs, qic, qjc, u, kk, gtol=1e-4)
+    dt = (time.perf_counter() - t0) / nsample
+    out = {"impl": "reference", "metric": "batched_dimer_minimisations_per_s", "value": 1.0 / dt, "unit": "systems/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * 10000,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "imidazole_dimers_10000_seed5", "systems": 10000, "sites_per_system": 18},
+           "cpu_baseline": {"value": 1.0 / dt, "unit": "systems/s", "cores": 1, "kind": "port",
+                            "sample": f"{nsample} of 10000 dimers, oracle/uind_dense.py + SciPy BFGS (stand-in for jaxopt), sequential"},
+           "e2e": {"value": 1.0 / dt, "unit": "systems/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
 
-    def max_over_ranks(x):
-        if world == 1:
+
+class Dist:
+    """torch.distributed plumbing shared by the configs."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=self.dev)   # > 126 MB L2
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t[0])
 
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+    def timed_steps(self, step, steps, warmup):
+        """W untimed warm-ups, then K steps timed with CUDA events, L2 flushed (untimed) between them;
+        returns (ms per step, max over ranks; wall seconds of the timed region; clock summary)."""
+        torch = self.torch
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        with ClockSampler(self.local_rank) as clk:
+            t0 = time.perf_counter()
+            for i in range(steps):
+                self.flush.fill_(float(i))            # L2 flush between timed iterations (not timed)
+                if self.world > 1:
+                    self.dist.barrier()
+                ev[i][0].record()
+                step()
+                ev[i][1].record()
+            self.barrier()
+            wall = time.perf_counter() - t0
+        ms = self.max_over_ranks(float(np.sum([a.elapsed_time(b) for a, b in ev])) / steps)
+        return ms, wall, clk.summary()
 
-    def step():
-        sysm.invalidate_static()              # do ALL the work of an evaluation every step
-        return sysm.energy_grad(d_dev, precision="fp64")
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
 
-    # ---- device-resident steps -----------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        e, g = step()
-    barrier()
-    sysm.set_kernel_timing(True)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clk:
-        t_wall0 = time.perf_counter()
-        for i in range(args.steps):
-            flush.fill_(float(i))             # L2 flush between timed iterations (not timed)
-            if world > 1:
-                dist.barrier()
-            ev[i][0].record()
-            e, g = step()
-            ev[i][1].record()
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-    ms_steps = [a.elapsed_time(b) for a, b in ev]
-    ms_per_step = max_over_ranks(float(np.sum(ms_steps)) / args.steps)
-    k_ms, k_n = sysm.kernel_time()
-    sysm.set_kernel_timing(False)
-    value = pairs_per_step / (ms_per_step * 1e-3)
-    e_host = e.cpu().numpy()
 
-    # ---- end to end through the C ABI with host buffers (H2D of r and d, D2H of E and grad) --
-    # page-locked host buffers (the contract: inputs come from pinned host memory)
+def _e2e_energy_grad(D, sysm, s, d_host, precision_code, steps):
+    """The same step through the C ABI with page-locked HOST buffers: H2D of r and d, D2H of E and grad inside."""
+    from u_pol_b200 import _lib as L
+
+    torch = D.torch
+    n = s.nmol * s.natoms
     r_pin = torch.from_numpy(np.ascontiguousarray(s.r_core.reshape(-1))).pin_memory()
     d_pin = torch.from_numpy(np.ascontiguousarray(d_host.reshape(-1))).pin_memory()
     e_pin = torch.empty(L.E_SIZE, dtype=torch.float64).pin_memory()
@@ -278,109 +338,344 @@ def run_cuda(args):
 
     def e2e_step():
         L.check(lib.upol_system_set_positions(sysm._h, r_host.ctypes.data, None))
-        L.check(lib.upol_uind_energy_grad_host(sysm._h, d_flat.ctypes.data, L.FP64, e_out.ctypes.data, g_out.ctypes.data))
+        L.check(lib.upol_uind_energy_grad_host(sysm._h, d_flat.ctypes.data, precision_code, e_out.ctypes.data, g_out.ctypes.data))
 
-    with torch.cuda.device(dev):
+    with torch.cuda.device(D.dev):
         for _ in range(2):
             e2e_step()
-        barrier()
-        n_e2e = max(3, min(args.steps, 10))
+        D.barrier()
+        n_e2e = max(3, min(steps, 10))
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             e2e_step()
-        barrier()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) / n_e2e * 1e3)
-    e2e_value = pairs_per_step / (e2e_ms * 1e-3)
-    assert abs(e_out[0] - e_host[0]) <= 1e-9 * abs(e_host[0]), (e_out[0], e_host[0])
+        D.barrier()
+        ms = D.max_over_ranks((time.perf_counter() - t0) / n_e2e * 1e3)
+    return ms, int(r_host.nbytes + d_flat.nbytes), int(g_out.nbytes + e_out.nbytes), e_out.copy(), g_out.copy()
 
-    # ---- minimisation wall time (second half of the metric) --------------------------------
-    minimise = {}
-    for prec in ("fp64", "mixed"):
-        sysm.minimize(tol=1e-4, precision=prec, maxiter=3)           # warm the workspace
-        barrier()
-        t0 = time.perf_counter()
-        _, info = sysm.minimize(tol=1e-4, precision=prec)
-        torch.cuda.synchronize()
-        wall = max_over_ranks(time.perf_counter() - t0)
-        minimise[prec] = {"wall_s": wall, "iterations": info["iterations"], "evaluations": info["evaluations"],
-                          "U_ind": info["U_ind"], "gnorm": info["gnorm"], "flags": info["flags"], "tol": 1e-4}
 
-    # ---- roofline of the dominant kernel (pair_fp64_kernel<POT,GRAD>) ----------------------
-    peak64 = measure_fma_peak(True, local_rank)
-    peak32 = measure_fma_peak(False, local_rank)
-    k_ms_avg = k_ms / max(k_n, 1)
-    achieved = FLOP_PER_INTERACTION * inter_local / (k_ms_avg * 1e-3) / 1e12
-    traffic = pipe_ncu = None
-    tfile = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tfile):
-        try:
-            tj = json.load(open(tfile))
-            traffic = tj.get("pair_fp64_kernel_dram_bytes_per_launch")
-            pipe_ncu = tj.get("pair_fp64_kernel_fp64_pipe_active_pct")      # from the committed ncu capture, not live
-        except Exception:
-            traffic = pipe_ncu = None
-    # mixed-precision field kernel, for context
+def _kernel_ms(sysm, fn, reps=5):
+    """CUDA-event time of the pair kernel alone (the library brackets its launch), averaged over `reps`."""
+    import torch
+
     sysm.set_kernel_timing(True)
-    for _ in range(3):
-        sysm.energy_grad(d_dev, precision="mixed", want_energy=False)
+    for _ in range(2):
+        fn()
     torch.cuda.synchronize()
     sysm.kernel_time()
-    for _ in range(5):
-        sysm.energy_grad(d_dev, precision="mixed", want_energy=False)
-    mx_ms, mx_n = sysm.kernel_time()
+    for _ in range(reps):
+        fn()
+    ms, k = sysm.kernel_time()
     sysm.set_kernel_timing(False)
-    mixed_tflops = FLOP_PER_INTERACTION * inter_local / (mx_ms / max(mx_n, 1) * 1e-3) / 1e12
+    return ms / max(k, 1), k
 
-    # kernels of ours launched per step: static pass (pair, finalize, reduce), main pass (gather,
-    # prepare, pair, finalize, reduce, assemble, scatter) [+ assemble after the all-reduce]
-    launches_per_step = 10 + (1 if world > 1 else 0)
+
+def _ncu_constants():
+    """Figures that only a profiler run can give (committed with the capture they come from, not live)."""
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(tfile))
+    except Exception:
+        return {}
+
+
+def run_energy_grad(args):
+    """Configs 4 (headline) and 2: full U_ind + gradient steps."""
+    import torch
+
+    from u_pol_b200 import _lib as L
+    from u_pol_b200.engine import UindSystem, measure_fma_peak
+
+    D = Dist()
+    s, d_host, workload = _config_workload(args.config)
+    n = s.nmol * s.natoms
+    nd = int((s.q_shell != 0).sum())
+    sysm = UindSystem.from_drude_system(s, device=D.local_rank)
+    exchange = "none"
+    if D.world > 1:
+        sysm.attach_process_group()
+        exchange = ("peer-memory stores (CUDA IPC/NVLink) fused into the finalize / update kernels"
+                    if getattr(sysm, "p2p", False) else "nccl")
+    d_dev = torch.as_tensor(d_host.reshape(-1)).to(D.dev)
+    pairs_per_step = n * (n - 1)
+    inter_local, inter_static_local = sysm.interactions(False), sysm.interactions(True)
+    n_d_mol = int((s.q_shell[0] != 0).sum())
+    inter_total = s.nmol * n_d_mol * ((n - s.natoms) + (nd - n_d_mol))          # I_inter, SURVEY 8d
+    inter_static_total = s.nmol * n_d_mol * (n - s.natoms)
+    warmup = max(args.warmup, 3)
+
+    def step64():
+        sysm.invalidate_static()              # do ALL the work of an evaluation every step
+        return sysm.energy_grad(d_dev, precision="fp64")
+
+    def stepmx():
+        return sysm.energy_grad(d_dev, precision="mixed")
+
+    # ---- fp64 headline: device-resident steps ------------------------------------------------
+    l0 = sysm.launch_count()
+    ms_per_step, t_wall, clocks = D.timed_steps(step64, args.steps, warmup)
+    launches = (sysm.launch_count() - l0) * args.steps // (args.steps + warmup)
+    e, g = step64()
+    e_host, g_dev = e.cpu().numpy(), g
+    value = pairs_per_step / (ms_per_step * 1e-3)
+    k64_ms, k64_n = _kernel_ms(sysm, step64)
+    e2e_ms, h2d, d2h, e_out, _ = _e2e_energy_grad(D, sysm, s, d_host, L.FP64, args.steps)
+    assert abs(e_out[0] - e_host[0]) <= 1e-9 * abs(e_host[0]), (e_out[0], e_host[0])
+
+    # ---- the same step in mixed precision (one fp32 difference-form pass) -----------------------
+    mx_ms, _, _ = D.timed_steps(stepmx, args.steps, warmup)
+    em, gm = stepmx()
+    kmx_ms, _ = _kernel_ms(sysm, stepmx)
+    mx_e2e_ms, _, _, emx_out, _ = _e2e_energy_grad(D, sysm, s, d_host, L.MIXED, args.steps)
+    kfield_ms, _ = _kernel_ms(sysm, lambda: sysm.energy_grad(d_dev, precision="mixed", want_energy=False))
+    mixed_err = {"U_ind_rel": abs(float(em[0]) - float(e_host[0])) / abs(float(e_host[0])),
+                 "grad_max_rel": float((gm - g_dev).abs().max() / g_dev.abs().max())}
+    assert mixed_err["U_ind_rel"] <= 1e-5 and mixed_err["grad_max_rel"] <= 1e-5, mixed_err
+
+    # ---- minimisation wall time (second half of the metric; config 4 only) -------------------------
+    minimise = {}
+    if args.config == 4:
+        for prec in ("fp64", "mixed"):
+            sysm.minimize(tol=1e-4, precision=prec, maxiter=3)           # warm the workspace
+            D.barrier()
+            t0 = time.perf_counter()
+            _, info = sysm.minimize(tol=1e-4, precision=prec)
+            torch.cuda.synchronize()
+            wall = D.max_over_ranks(time.perf_counter() - t0)
+            minimise[prec] = {"wall_s": wall, "iterations": info["iterations"], "evaluations": info["evaluations"],
+                              "U_ind": info["U_ind"], "gnorm": info["gnorm"], "flags": info["flags"], "tol": 1e-4}
+
+    # ---- parity against the committed N=1 values (multi-GPU correctness visible to the driver) -----
+    parity = None
+    if args.config == 4 and NMOL == 20000:
+        rng = np.random.default_rng(11)
+        rows = np.sort(rng.choice(n, 64, replace=False))
+        cur = {"U_ind": float(e_host[0]), "g2": float((g_dev.double() ** 2).sum()),
+               "grad_rows": g_dev[torch.as_tensor(rows, device=D.dev)].cpu().numpy().tolist(), "rows": rows.tolist(),
+               "gmax": float(g_dev.abs().max()),
+               "U_min": minimise["fp64"]["U_ind"] if minimise else None}
+        if args.write_parity and D.rank == 0 and D.world == 1:
+            json.dump(cur, open(PARITY_FILE, "w"))
+        if os.path.isfile(PARITY_FILE):
+            ref = json.load(open(PARITY_FILE))
+            dg = float(np.abs(np.array(cur["grad_rows"]) - np.array(ref["grad_rows"])).max())
+            parity = {"against": "tests/golden/bench_parity_config4.json (N=1 run of this workload)",
+                      "U_ind_rel": abs(cur["U_ind"] - ref["U_ind"]) / abs(ref["U_ind"]),
+                      "g2_rel": abs(cur["g2"] - ref["g2"]) / abs(ref["g2"]),
+                      "grad_rows_max_rel": dg / ref["gmax"],
+                      "U_min_rel": abs(cur["U_min"] - ref["U_min"]) / abs(ref["U_min"]) if minimise else None,
+                      "tolerances": {"U_ind_rel": 1e-12, "g2_rel": 1e-12, "grad_rows_max_rel": 1e-12, "U_min_rel": 1e-10}}
+            ok = (parity["U_ind_rel"] <= 1e-12 and parity["g2_rel"] <= 1e-12 and parity["grad_rows_max_rel"] <= 1e-12
+                  and (parity["U_min_rel"] is None or parity["U_min_rel"] <= 1e-10))
+            parity["ok"] = bool(ok)
+            assert ok, parity
+
+    # ---- rooflines ------------------------------------------------------------------------------
+    peak64 = measure_fma_peak(True, D.local_rank)
+    peak32 = measure_fma_peak(False, D.local_rank)
+    flops_full_local = FLOP_PER_INTERACTION * inter_local + FLOP_PER_STATIC_INTERACTION * inter_static_local
+    achieved = flops_full_local / (k64_ms * 1e-3) / 1e12
+    ncu = _ncu_constants()
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, rows, dt = cpu_sample(s, d_host, target_seconds=12.0)
+    if D.rank == 0 and D.world == 1 and not args.no_cpu:
+        v, cores, rows_c, dt = cpu_sample(s, d_host, target_seconds=12.0)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{rows} of {n} site rows x all columns, one E+grad pass, {dt:.1f} s, "
+                        "sample": f"{rows_c} of {n} site rows x all columns, one E+grad pass, {dt:.1f} s, "
                                   "oracle/uind_oracle.c (C restatement of polarization.py, OpenMP)"}
 
-    if rank == 0:
+    if D.rank == 0:
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": D.world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sites": n, "drudes": nd, "parallelism": f"row-shard x{world}",
+            "config": {"workload": workload, "sites": n, "drudes": nd, "parallelism": f"row-shard x{D.world}",
                        "l2": "flushed between timed steps (256 MiB write, untimed)",
-                       "step": "full U_ind + grad incl. recomputed static part",
-                       "minimiser_exchange": exchange},
+                       "step": "full fp64 U_ind + grad incl. the static part (recomputed every step, fused into the pass)",
+                       "exchange": exchange},
             "interactions_per_s": (inter_total + inter_static_total) / (ms_per_step * 1e-3),
             "U_ind": float(e_host[0]),
             "wall_s_timed_region": t_wall,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(r_host.nbytes + d_flat.nbytes),
-                    "d2h_bytes_per_step": int(g_out.nbytes + e_out.nbytes)},
-            "gpu_launches": launches_per_step * args.steps,
-            "clocks": clk.summary(),
-            "roofline": {"bound": "fp64", "kernel": "pair_fp64_kernel<POT,GRAD>", "achieved": achieved,
-                         "peak": peak64 / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak64 / 1e12),
-                         "peak_source": "measured on this box: upol_measure_fma_peak (DFMA chain); "
+            "e2e": {"value": pairs_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "gpu_launches_per_step": int(launches // max(args.steps, 1)),
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "kernel": "pair_fp64_kernel<POT,GRAD,FUSE> (main pass + fused static potential)",
+                         "achieved": achieved, "peak": peak64 / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak64 / 1e12),
+                         "peak_source": "measured on this box: upol_measure_fma_peak (DFMA chain = what the FP64 pipe sustains: "
+                                        "91.6 % of the rate ncu calls 100 %, profiles/r02_ubench_ncu_summary.txt); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
-                         "kernel_ms": k_ms_avg, "launches_timed": k_n,
-                         "interactions_per_launch": inter_local, "flop_per_interaction": FLOP_PER_INTERACTION,
-                         # the kernel issues 18.3 FP64-pipe instructions per interaction (SASS count: DFMA, DADD, DMUL;
-                         # DESIGN section 5): share of the DFMA-chain issue rate those instructions take up
-                         "fp64_instr_per_interaction": 18.3,
-                         "fp64_issue_frac": 18.3 * inter_local / (k_ms_avg * 1e-3) / (peak64 / 2.0),
-                         "fp64_pipe_active_pct_ncu": pipe_ncu,
-                         "traffic": traffic,
-                         "mixed_field_kernel": {"achieved": mixed_tflops, "peak": peak32 / 1e12,
-                                                "frac": mixed_tflops / (peak32 / 1e12), "unit": "TFLOP/s"}},
-            "minimise": minimise,
+                         "kernel_ms": k64_ms, "launches_timed": k64_n,
+                         "flops_per_launch": flops_full_local,
+                         "interactions_per_launch": inter_local, "static_interactions_per_launch": inter_static_local,
+                         "flop_per_interaction": FLOP_PER_INTERACTION, "flop_per_static_interaction": FLOP_PER_STATIC_INTERACTION,
+                         "fp64_pipe_active_pct_ncu": ncu.get("pair_fp64_kernel_fp64_pipe_active_pct"),
+                         "traffic": ncu.get("pair_fp64_kernel_dram_bytes_per_launch"),
+                         "traffic_source": ncu.get("source")},
+            "mixed_step": {"ms_per_step": mx_ms, "value": pairs_per_step / (mx_ms * 1e-3), "unit": UNIT,
+                           "e2e_ms_per_step": mx_e2e_ms, "kernel": "pair_diff_kernel<POT> (energy + field, difference form)",
+                           "kernel_ms": kmx_ms, "achieved": flops_full_local / (kmx_ms * 1e-3) / 1e12, "peak": peak32 / 1e12,
+                           "unit_roofline": "TFLOP/s", "frac": flops_full_local / (kmx_ms * 1e-3) / peak32,
+                           "bound": "fp32 register-operand bandwidth (2 x 32-bit reads per lane and cycle; FMAs with three "
+                                    "live operands cannot exceed 2/3 of the FFMA-chain peak, profiles/r02_ubench.txt)",
+                           "fma_pipe_active_pct_ncu": ncu.get("pair_diff_kernel_fma_pipe_active_pct"),
+                           "xu_pipe_active_pct_ncu": ncu.get("pair_diff_kernel_xu_pipe_active_pct"),
+                           "traffic": ncu.get("pair_diff_kernel_dram_bytes_per_launch"),
+                           "field_only_kernel_ms": kfield_ms,
+                           "field_only_achieved": FLOP_PER_INTERACTION * inter_local / (kfield_ms * 1e-3) / 1e12,
+                           "field_only_frac": FLOP_PER_INTERACTION * inter_local / (kfield_ms * 1e-3) / peak32,
+                           "error_vs_fp64": mixed_err, "U_ind": float(em[0]), "U_ind_e2e": float(emx_out[0])},
         }
+        if minimise:
+            out["minimise"] = minimise
+        if parity is not None:
+            out["parity"] = parity
         if cpu_baseline is not None:
             out["cpu_baseline"] = cpu_baseline
         print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
+
+
+def run_minimise(args):
+    """Config 3: full minimisation of the 20 k-Drude box on one GPU (row-sharded at N>1); a step = one
+    minimisation from d = 0 to ||grad||_2 <= 1e-4; value = wall seconds per minimisation."""
+    import ctypes as C
+
+    import torch
+
+    from u_pol_b200 import _lib as L
+    from u_pol_b200.engine import UindSystem
+
+    D = Dist()
+    s, _, workload = _config_workload(3)
+    n = s.nmol * s.natoms
+    nd = int((s.q_shell != 0).sum())
+    sysm = UindSystem.from_drude_system(s, device=D.local_rank)
+    if D.world > 1:
+        sysm.attach_process_group()
+    infos = []
+
+    def step():
+        infos.append(sysm.minimize(tol=1e-4, precision=args.precision)[1])
+
+    warmup = max(args.warmup, 3)
+    l0 = sysm.launch_count()
+    ms, wall, clocks = D.timed_steps(step, args.steps, warmup)
+    launches = (sysm.launch_count() - l0) * args.steps // (args.steps + warmup)
+    info = infos[-1]
+    assert info["flags"] == 0 and info["gnorm"] <= 1e-4, info
+    # end to end through the C ABI with host buffers: positions up, zeros up, minimiser down
+    r_host = np.ascontiguousarray(s.r_core.reshape(-1))
+    d_host = np.zeros(3 * n)
+    o = L.MinOptions()
+    L.lib().upol_min_options_default(C.byref(o))
+    o.tol, o.precision = 1e-4, {"fp64": L.FP64, "mixed": L.MIXED}[args.precision]
+    res = L.MinResult()
+
+    def e2e_step():
+        d_host[:] = 0.0
+        L.check(L.lib().upol_system_set_positions(sysm._h, r_host.ctypes.data, None))
+        L.check(L.lib().upol_minimize_host(sysm._h, d_host.ctypes.data, C.byref(o), C.byref(res)))
+
+    with torch.cuda.device(D.dev):
+        for _ in range(2):
+            e2e_step()
+        D.barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(3, min(args.steps, 10))):
+            e2e_step()
+        D.barrier()
+        e2e_ms = D.max_over_ranks((time.perf_counter() - t0) / max(3, min(args.steps, 10)) * 1e3)
+    assert abs(res.energy[0] - info["U_ind"]) <= 1e-9 * abs(info["U_ind"])
+    cpu_baseline = None
+    if D.rank == 0 and D.world == 1 and not args.no_cpu:
+        from u_pol_b200 import synth
+
+        v, cores, rows_c, dt = cpu_sample(s, synth.random_displacements(s, seed=4), target_seconds=10.0)
+        cpu_baseline = {"value": info["evaluations"] * n * (n - 1) / v, "unit": "s", "cores": cores, "kind": "port",
+                        "sample": f"{info['evaluations']} evaluations x one full E+grad pass of oracle/uind_oracle.c extrapolated "
+                                  f"from {rows_c} of {n} site rows ({dt:.1f} s measured)"}
+    if D.rank == 0:
+        out = {"metric": "uind_minimise_wall_s", "value": ms * 1e-3, "unit": "s", "n_gpus": D.world, "steps": args.steps,
+               "warmup": warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f64" if args.precision == "fp64" else "f32 pairs / f64 accumulation", "data": "synthetic",
+               "config": {"workload": workload, "sites": n, "drudes": nd, "tol": 1e-4, "precision": args.precision,
+                          "l2": "flushed between timed steps (256 MiB write, untimed)", "parallelism": f"row-shard x{D.world}"},
+               "iterations": info["iterations"], "evaluations": info["evaluations"], "U_ind": info["U_ind"], "gnorm": info["gnorm"],
+               "ms_per_evaluation_slot": ms / info["evaluations"],
+               "e2e": {"value": e2e_ms * 1e-3, "unit": "s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(r_host.nbytes + d_host.nbytes),
+                       "d2h_bytes_per_step": int(d_host.nbytes)},
+               "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall}
+        if cpu_baseline is not None:
+            out["cpu_baseline"] = cpu_baseline
+        print(json.dumps(out), flush=True)
+    D.close()
+
+
+def run_batched(args):
+    """Config 5: 10 000 independent imidazole dimers minimised in one launch (replicas only at N>1: every rank
+    takes its share of the batch, no data-path collective)."""
+    import torch
+
+    from u_pol_b200.engine import batched_minimize
+
+    D = Dist()
+    nbatch = 10000
+    z, r, k = _dimer_batch(nbatch)
+    lo, hi = nbatch * D.rank // D.world, nbatch * (D.rank + 1) // D.world
+    r_dev = torch.as_tensor(r[lo:hi]).to(D.dev)
+    out_box = {}
+
+    def step():
+        out_box["res"] = batched_minimize(r_dev, z["q_core"], z["q_shell"], k, z["thole_u"], tol=1e-4)
+
+    warmup = max(args.warmup, 3)
+    ms, wall, clocks = D.timed_steps(step, args.steps, warmup)
+    d, e, it = out_box["res"]
+    assert not bool(e[:, 6].any()), "a dimer did not minimise cleanly"
+    # parity inside the run: the 312 reference geometries against the reference's own recorded minima
+    # (tests/imidazole/induction_data.csv, within the reference's convergence scatter)
+    parity = None
+    if D.rank == 0:
+        r312 = z["r_core"].astype(np.float32).astype(np.float64)      # as the reference saw them (OpenMM CPU platform)
+        d3, e3, _ = batched_minimize(torch.as_tensor(r312).to(D.dev), z["q_core"], z["q_shell"], k, z["thole_u"], tol=1e-6)
+        u, ref = e3[:, 0].cpu().numpy(), z["md_induction"]
+        rel = np.abs(u - ref) / np.abs(ref)
+        parity = {"systems": int(len(u)), "median_rel": float(np.median(rel)), "max_rel": float(rel.max()),
+                  "within_1e-5": int((rel < 1e-5).sum()),
+                  "against": "tests/golden/dimers312.npz: minimised U_ind recorded by the reference (induction_data.csv); "
+                             "the reference's own convergence scatter is ~1e-6 median / 5e-4 max"}
+        assert parity["median_rel"] < 1e-6 and parity["max_rel"] < 5e-4 and parity["within_1e-5"] >= 285, parity
+    # end to end: host geometries in, host energies out
+    r_host = np.ascontiguousarray(r[lo:hi])
+
+    def e2e_step():
+        _, e2, _ = batched_minimize(torch.from_numpy(r_host), z["q_core"], z["q_shell"], k, z["thole_u"], tol=1e-4)
+        return e2[:, 0].cpu().numpy()
+
+    for _ in range(2):
+        e2e_step()
+    D.barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        u_host = e2e_step()
+    D.barrier()
+    e2e_ms = D.max_over_ranks((time.perf_counter() - t0) / 5 * 1e3)
+    if D.rank == 0:
+        out = {"metric": "batched_dimer_minimisations_per_s", "value": nbatch / (ms * 1e-3), "unit": "systems/s",
+               "n_gpus": D.world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "imidazole_dimers_10000_seed5", "systems": nbatch, "sites_per_system": 18,
+                          "drudes_per_system": 10, "tol": 1e-4, "parallelism": f"replicas x{D.world}",
+                          "l2": "flushed between timed steps (256 MiB write, untimed)"},
+               "iterations_mean": float(it.float().mean()), "iterations_max": int(it.max()),
+               "e2e": {"value": nbatch / (e2e_ms * 1e-3), "unit": "systems/s", "ms_per_step": e2e_ms,
+                       "h2d_bytes_per_step": int(r_host.nbytes), "d2h_bytes_per_step": int(u_host.nbytes)},
+               "gpu_launches": args.steps, "clocks": clocks, "wall_s_timed_region": wall}
+        if parity is not None:
+            out["parity"] = parity
+        print(json.dumps(out), flush=True)
+    D.close()
 
 
 def main():
@@ -389,12 +684,21 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config (4 = the headline, default)")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "mixed"], help="config 3 only")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--write-parity", action="store_true",
+                    help="N=1, config 4: (re)write tests/golden/bench_parity_config4.json from this run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config in (2, 4):
+        run_energy_grad(args)
+    elif args.config == 3:
+        run_minimise(args)
     else:
-        run_cuda(args)
+        run_batched(args)
 
 
 if __name__ == "__main__":

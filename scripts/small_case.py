@@ -1,28 +1,46 @@
-"""Host enqueue time vs device time of one evaluation at config-2 size (3000 waters)."""
+"""Config 2 (3000 waters) and config 3 (4000 imidazoles): where does the time of one evaluation go?
+Per kind of evaluation: wall time per call when every call is synchronised (latency, includes the host side),
+per call in a batch of 50 enqueued back to back (device-side pipeline), and the CUDA-event time of the pair
+kernel alone (the library's own events)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from u_pol_b200 import synth
 from u_pol_b200.engine import UindSystem
-s = synth.water_box(3000, seed=2)
-sysm = UindSystem.from_drude_system(s)
-D = torch.as_tensor(synth.random_displacements(s, seed=1).reshape(-1)).cuda()
-def run(label, fn, n=200):
+
+def bench(sysm, D, label, **kw):
+    inval = kw.pop("invalidate", False)
+    def fn():
+        if inval: sysm.invalidate_static()
+        return sysm.energy_grad(D, **kw)
     for _ in range(5): fn()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(n): fn()
-    t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
-    print(f"{label}: enqueue {(t1 - t0) / n * 1e6:.1f} us/eval, total {(t2 - t0) / n * 1e6:.1f} us/eval", flush=True)
-run("fp64 E+grad", lambda: sysm.energy_grad(D))
-run("fp64 grad only", lambda: sysm.energy_grad(D, want_energy=False))
-run("fp64 E only", lambda: sysm.energy_grad(D, want_grad=False))
-run("mixed grad only", lambda: sysm.energy_grad(D, precision="mixed", want_energy=False))
-def full():
-    sysm.invalidate_static(); sysm.energy_grad(D)
-run("fp64 E+grad, static recomputed", full)
-run("fp64 E+grad again", lambda: sysm.energy_grad(D))
-d, info = sysm.minimize(tol=1e-4)
-for _ in range(3):
-    t0 = time.perf_counter(); d, info = sysm.minimize(tol=1e-4); torch.cuda.synchronize()
-    print("minimise %.2f ms" % ((time.perf_counter() - t0) * 1e3), info["evaluations"], flush=True)
+    for _ in range(50):
+        fn(); torch.cuda.synchronize()
+    lat = (time.perf_counter() - t0) / 50
+    t0 = time.perf_counter()
+    for _ in range(50): fn()
+    torch.cuda.synchronize()
+    thr = (time.perf_counter() - t0) / 50
+    sysm.set_kernel_timing(True)
+    for _ in range(20): fn()
+    ms, n = sysm.kernel_time()
+    sysm.set_kernel_timing(False)
+    print(f"  {label:34s} latency {lat*1e6:7.1f} us   back-to-back {thr*1e6:7.1f} us   pair kernel {ms/max(n,1)*1e3:7.1f} us ({n} launches)")
+
+for name, maker, nmol, seed in (("config 2: 3000 waters", synth.water_box, 3000, 2), ("config 3: 4000 imidazoles", synth.imidazole_box, 4000, 3)):
+    s = maker(nmol, seed=seed)
+    sysm = UindSystem.from_drude_system(s)
+    D = torch.as_tensor(synth.random_displacements(s, seed=1).reshape(-1)).cuda()
+    print(name, f"N={s.nmol*s.natoms} N_D={sysm.ndrude}")
+    bench(sysm, D, "fp64 E+grad, static recomputed", invalidate=True)
+    bench(sysm, D, "fp64 E+grad, static cached")
+    bench(sysm, D, "fp64 field only", want_energy=False)
+    bench(sysm, D, "mixed E+grad", precision="mixed")
+    bench(sysm, D, "mixed field only", precision="mixed", want_energy=False)
+    for prec in ("fp64", "mixed"):
+        sysm.minimize(tol=1e-4, precision=prec, maxiter=2)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        d, info = sysm.minimize(tol=1e-4, precision=prec); torch.cuda.synchronize(); t = time.perf_counter() - t0
+        print(f"  minimise {prec:5s}: {t*1e3:.2f} ms, {info['iterations']} it / {info['evaluations']} evals -> {t/info['evaluations']*1e6:.0f} us per evaluation slot, U = {info['U_ind']:.6f}")

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libupol_b200.so")
+# UPOL_B200_LIB points at another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("UPOL_B200_LIB") or os.path.join(_HERE, "lib", "libupol_b200.so")
 
 E_UIND, E_INTER, E_INTRA, E_SELF, E_GNORM2, E_STATIC, E_SIZE = 0, 1, 2, 3, 4, 5, 8
 FP64, MIXED = 0, 1

@@ -39,6 +39,8 @@
 //
 // FMA-pipe instructions per (row, polarisable site): 45 with the energy, 26 field only; per (row,
 // other site) 23 / 12; MUFU 5 / 2 and 3 / 1.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "f32x2.cuh"
 
@@ -49,6 +51,7 @@ namespace {
 constexpr float kDropNm = 1.0e-5f;        // distances below this count as zero (term dropped)
 constexpr float kBigFieldNm = 1.0e6f;     // e/nm^2: a tile partial beyond this had a (near-)zero distance
 constexpr float kBigPotNm = 1.0e4f;       // e/nm
+constexpr int kFarFix = (1 << 30) - 1;    // fixed-point coordinate of the zero-charge padding columns (system.cu)
 
 struct DiffConsts {
     float thr2;        // (kDropNm * inv_grid)^2, grid units^2
@@ -104,7 +107,106 @@ __device__ __forceinline__ void diff_site_careful(const int4 c, const float4 cd,
 
 }  // namespace
 
-template <int ROWS, bool POT, int MINB>
+// Packed tile loops.  MASKED: the tile overlaps the same-molecule interval of some row of the warp; the excluded
+// (row, column) pairs are then switched off lane by lane - zero charges, and the column moved to the far corner so
+// that every distance in the lane stays finite and benign (a row's own site would otherwise sit at |A| = |d_i|,
+// which is exactly 0 at the start of a minimisation) - at the price of ~10 integer-pipe instructions per site; the
+// arithmetic is the packed one either way.
+template <int NP, bool POT, bool MASKED, int UNR>
+__device__ __forceinline__ void diff_tile_P(const int4 *__restrict__ shX, const float4 *__restrict__ shD, const float *__restrict__ shD2,
+                                            const int *sx, const int *sy, const int *sz, const int *lo, const int *len,
+                                            const f32x2 *T2x, const f32x2 *T2y, const f32x2 *T2z, const f32x2 *ND2,
+                                            f32x2 *Fx, f32x2 *Fy, f32x2 *Fz, f32x2 *Hx, f32x2 *Hy, f32x2 *Hz, f32x2 *PA, f32x2 *PC) {
+    const f32x2 mone2 = bcast2(-1.0f), m15 = bcast2(-1.5f);
+#pragma unroll UNR
+    for (int j = 0; j < kTileCols; ++j) {
+        const int4 c = shX[j];
+        const float4 cd = shD[j];
+        const float qc = __int_as_float(c.w), qs = cd.w;
+        const f32x2 mx2 = bcast2(cd.x), my2 = bcast2(cd.y), mz2 = bcast2(cd.z), dj2 = bcast2(shD2[j]);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            int cx0 = c.x, cx1 = c.x;
+            f32x2 qc2 = bcast2(qc), qs2 = bcast2(qs);
+            if (MASKED) {
+                const bool e0 = (unsigned)(j - lo[2 * p]) < (unsigned)len[2 * p], e1 = (unsigned)(j - lo[2 * p + 1]) < (unsigned)len[2 * p + 1];
+                cx0 = e0 ? kFarFix : c.x; cx1 = e1 ? kFarFix : c.x;
+                qc2 = pack2(e0 ? 0.f : qc, e1 ? 0.f : qc); qs2 = pack2(e0 ? 0.f : qs, e1 ? 0.f : qs);
+            }
+            const f32x2 Ax = pack2((float)(cx0 - sx[2 * p]), (float)(cx1 - sx[2 * p + 1]));
+            const f32x2 Ay = pack2((float)(c.y - sy[2 * p]), (float)(c.y - sy[2 * p + 1]));
+            const f32x2 Az = pack2((float)(c.z - sz[2 * p]), (float)(c.z - sz[2 * p + 1]));
+            const f32x2 A2 = fma2(Az, Az, fma2(Ay, Ay, mul2(Ax, Ax)));
+            const f32x2 yA = rsqrt2(A2);
+            const f32x2 pa = mul2(qc2, yA);
+            const f32x2 DCA = fma2(Ax, mx2, fma2(Ay, my2, fma2(Az, mz2, dj2)));         // |C|^2 - |A|^2
+            const f32x2 C2 = add2(A2, DCA);
+            const f32x2 yC = rsqrt2(C2);
+            const f32x2 pc = mul2(qs2, yC);
+            if (POT) {
+                const f32x2 DA = fma2(Ax, T2x[p], fma2(Ay, T2y[p], fma2(Az, T2z[p], ND2[p])));  // |A|^2 - |R|^2
+                const f32x2 R2 = sub2(A2, DA);
+                const f32x2 DC = add2(DA, DCA);                                         // |C|^2 - |R|^2
+                const f32x2 yR = rsqrt2(R2);
+                const f32x2 nR = mul2(R2, yR);
+                const f32x2 uA = mul2(yR, rcp2(fma2(A2, yA, nR)));
+                const f32x2 uC = mul2(yR, rcp2(fma2(C2, yC, nR)));
+                PA[p] = fma2(pa, mul2(DA, uA), PA[p]);        // -qc [f(A) - f(R)]
+                PC[p] = fma2(pc, mul2(DC, uC), PC[p]);        // -qs [f(C) - f(R)]
+            }
+            const f32x2 yA2 = mul2(yA, yA), yC2 = mul2(yC, yC);
+            const f32x2 meA = fma2(A2, yA2, mone2), meC = fma2(C2, yC2, mone2);      // -(1 - |X|^2 y^2)
+            const f32x2 zA = mul2(pa, yA2), zC = mul2(pc, yC2);
+            // w_A + w_C with both seed corrections in one go; the -w_C d_j part is |d_j|/|A| times
+            // smaller than the gross terms and takes the uncorrected z_C
+            const f32x2 wS = fma2(fma2(zC, meC, mul2(zA, meA)), m15, add2(zA, zC));
+            Fx[p] = fma2(wS, Ax, Fx[p]); Fy[p] = fma2(wS, Ay, Fy[p]); Fz[p] = fma2(wS, Az, Fz[p]);
+            Hx[p] = fma2(zC, mx2, Hx[p]); Hy[p] = fma2(zC, my2, Hy[p]); Hz[p] = fma2(zC, mz2, Hz[p]);
+        }
+    }
+}
+
+template <int NP, bool POT, bool MASKED, int UNR>
+__device__ __forceinline__ void diff_tile_N(const int4 *__restrict__ shX, const int *sx, const int *sy, const int *sz,
+                                            const int *lo, const int *len, const f32x2 *T2x, const f32x2 *T2y,
+                                            const f32x2 *T2z, const f32x2 *ND2, f32x2 *Fx, f32x2 *Fy, f32x2 *Fz, f32x2 *PA) {
+    const f32x2 mone2 = bcast2(-1.0f), m15 = bcast2(-1.5f);
+#pragma unroll UNR
+    for (int j = 0; j < kTileCols; ++j) {
+        const int4 c = shX[j];
+        const float qc = __int_as_float(c.w);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            int cx0 = c.x, cx1 = c.x;
+            f32x2 qc2 = bcast2(qc);
+            if (MASKED) {
+                const bool e0 = (unsigned)(j - lo[2 * p]) < (unsigned)len[2 * p], e1 = (unsigned)(j - lo[2 * p + 1]) < (unsigned)len[2 * p + 1];
+                cx0 = e0 ? kFarFix : c.x; cx1 = e1 ? kFarFix : c.x;
+                qc2 = pack2(e0 ? 0.f : qc, e1 ? 0.f : qc);
+            }
+            const f32x2 Ax = pack2((float)(cx0 - sx[2 * p]), (float)(cx1 - sx[2 * p + 1]));
+            const f32x2 Ay = pack2((float)(c.y - sy[2 * p]), (float)(c.y - sy[2 * p + 1]));
+            const f32x2 Az = pack2((float)(c.z - sz[2 * p]), (float)(c.z - sz[2 * p + 1]));
+            const f32x2 A2 = fma2(Az, Az, fma2(Ay, Ay, mul2(Ax, Ax)));
+            const f32x2 yA = rsqrt2(A2);
+            const f32x2 pa = mul2(qc2, yA);
+            if (POT) {
+                const f32x2 DA = fma2(Ax, T2x[p], fma2(Ay, T2y[p], fma2(Az, T2z[p], ND2[p])));
+                const f32x2 R2 = sub2(A2, DA);
+                const f32x2 yR = rsqrt2(R2);
+                const f32x2 uA = mul2(yR, rcp2(fma2(A2, yA, mul2(R2, yR))));
+                PA[p] = fma2(pa, mul2(DA, uA), PA[p]);
+            }
+            const f32x2 yA2 = mul2(yA, yA);
+            const f32x2 meA = fma2(A2, yA2, mone2);
+            const f32x2 zA = mul2(pa, yA2);
+            const f32x2 wA = fma2(mul2(zA, meA), m15, zA);
+            Fx[p] = fma2(wA, Ax, Fx[p]); Fy[p] = fma2(wA, Ay, Fy[p]); Fz[p] = fma2(wA, Az, Fz[p]);
+        }
+    }
+}
+
+template <int ROWS, bool POT, int MINB, int UP, int UN>
 __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs a) {
     static_assert(ROWS % 2 == 0, "rows are processed in fp32 pairs");
     constexpr int NP = ROWS / 2;
@@ -144,7 +246,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
         loA[r] = a.exA_lo[i]; lenA[r] = a.exA_len[i];
         loB[r] = a.exB_lo[i]; lenB[r] = a.exB_len[i];
         fx[r] = fy[r] = fz[r] = 0.0;
-        if (POT) pA[r] = pC[r] = 0.0;
+        if (POT) pA[POT ? r : 0] = pC[POT ? r : 0] = 0.0;
     }
 
     const int t0 = (int)(((int64_t)a.n_tiles * blockIdx.y) / a.n_split);
@@ -170,94 +272,28 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
         }
         // tile-local fp32 sums: field g, potentials ph (cores, shells)
         float gx[ROWS], gy[ROWS], gz[ROWS], phc[ROWS], phs[ROWS];
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) gx[r] = gy[r] = gz[r] = phc[r] = phs[r] = 0.f;
-
-        bool careful = __any_sync(0xffffffffu, need);
-        if (!careful) {
-            const f32x2 mone2 = bcast2(-1.0f), m15 = bcast2(-1.5f), zero2 = bcast2(0.f);
+        bool bad = false;
+        {
+            const f32x2 zero2 = bcast2(0.f);
             f32x2 Fx[NP], Fy[NP], Fz[NP], Hx[NP], Hy[NP], Hz[NP], PA[NP], PC[NP];
 #pragma unroll
             for (int p = 0; p < NP; ++p) Fx[p] = Fy[p] = Fz[p] = Hx[p] = Hy[p] = Hz[p] = PA[p] = PC[p] = zero2;
+            // the row constants are kept as scalars (the pair-by-pair redo reads them) and paired up per tile
             f32x2 T2x[NP], T2y[NP], T2z[NP], ND2[NP];
-            if (POT) {
 #pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    T2x[p] = pack2(t2x[2 * p], t2x[2 * p + 1]); T2y[p] = pack2(t2y[2 * p], t2y[2 * p + 1]);
-                    T2z[p] = pack2(t2z[2 * p], t2z[2 * p + 1]); ND2[p] = pack2(nd2[2 * p], nd2[2 * p + 1]);
-                }
+            for (int p = 0; p < NP; ++p) {
+                T2x[p] = pack2(t2x[2 * p], t2x[2 * p + 1]); T2y[p] = pack2(t2y[2 * p], t2y[2 * p + 1]);
+                T2z[p] = pack2(t2z[2 * p], t2z[2 * p + 1]); ND2[p] = pack2(nd2[2 * p], nd2[2 * p + 1]);
             }
+            const bool masked = __any_sync(0xffffffffu, need);
             if (isP) {
-#pragma unroll 2
-                for (int j = 0; j < kTileCols; ++j) {
-                    const int4 c = shX[j];
-                    const float4 cd = shD[j];
-                    const f32x2 qc2 = bcast2(__int_as_float(c.w)), qs2 = bcast2(cd.w);
-                    const f32x2 mx2 = bcast2(cd.x), my2 = bcast2(cd.y), mz2 = bcast2(cd.z);
-                    const f32x2 dj2 = bcast2(shD2[j]);
-#pragma unroll
-                    for (int p = 0; p < NP; ++p) {
-                        const f32x2 Ax = pack2((float)(c.x - sx[2 * p]), (float)(c.x - sx[2 * p + 1]));
-                        const f32x2 Ay = pack2((float)(c.y - sy[2 * p]), (float)(c.y - sy[2 * p + 1]));
-                        const f32x2 Az = pack2((float)(c.z - sz[2 * p]), (float)(c.z - sz[2 * p + 1]));
-                        const f32x2 A2 = fma2(Az, Az, fma2(Ay, Ay, mul2(Ax, Ax)));
-                        const f32x2 yA = rsqrt2(A2);
-                        const f32x2 pa = mul2(qc2, yA);
-                        const f32x2 DCA = fma2(Ax, mx2, fma2(Ay, my2, fma2(Az, mz2, dj2)));   // |C|^2 - |A|^2
-                        const f32x2 C2 = add2(A2, DCA);
-                        const f32x2 yC = rsqrt2(C2);
-                        const f32x2 pc = mul2(qs2, yC);
-                        if (POT) {
-                            const f32x2 DA = fma2(Ax, T2x[p], fma2(Ay, T2y[p], fma2(Az, T2z[p], ND2[p])));  // |A|^2 - |R|^2
-                            const f32x2 R2 = sub2(A2, DA);
-                            const f32x2 DC = add2(DA, DCA);                                         // |C|^2 - |R|^2
-                            const f32x2 yR = rsqrt2(R2);
-                            const f32x2 nR = mul2(R2, yR);
-                            const f32x2 uA = mul2(yR, rcp2(fma2(A2, yA, nR)));
-                            const f32x2 uC = mul2(yR, rcp2(fma2(C2, yC, nR)));
-                            PA[p] = fma2(pa, mul2(DA, uA), PA[p]);    // -qc [f(A) - f(R)]
-                            PC[p] = fma2(pc, mul2(DC, uC), PC[p]);    // -qs [f(C) - f(R)]
-                        }
-                        const f32x2 yA2 = mul2(yA, yA), yC2 = mul2(yC, yC);
-                        const f32x2 meA = fma2(A2, yA2, mone2), meC = fma2(C2, yC2, mone2);      // -(1 - |X|^2 y^2)
-                        const f32x2 zA = mul2(pa, yA2), zC = mul2(pc, yC2);
-                        // w_A + w_C with both seed corrections in one go; the -w_C d_j part is |d_j|/|A| times
-                        // smaller than the gross terms and takes the uncorrected z_C
-                        const f32x2 wS = fma2(fma2(zC, meC, mul2(zA, meA)), m15, add2(zA, zC));
-                        Fx[p] = fma2(wS, Ax, Fx[p]); Fy[p] = fma2(wS, Ay, Fy[p]); Fz[p] = fma2(wS, Az, Fz[p]);
-                        Hx[p] = fma2(zC, mx2, Hx[p]); Hy[p] = fma2(zC, my2, Hy[p]); Hz[p] = fma2(zC, mz2, Hz[p]);
-                    }
-                }
+                if (masked) diff_tile_P<NP, POT, true, UP>(shX, shD, shD2, sx, sy, sz, lo, len, T2x, T2y, T2z, ND2, Fx, Fy, Fz, Hx, Hy, Hz, PA, PC);
+                else diff_tile_P<NP, POT, false, UP>(shX, shD, shD2, sx, sy, sz, lo, len, T2x, T2y, T2z, ND2, Fx, Fy, Fz, Hx, Hy, Hz, PA, PC);
             } else {
-#pragma unroll 4
-                for (int j = 0; j < kTileCols; ++j) {
-                    const int4 c = shX[j];
-                    const f32x2 qc2 = bcast2(__int_as_float(c.w));
-#pragma unroll
-                    for (int p = 0; p < NP; ++p) {
-                        const f32x2 Ax = pack2((float)(c.x - sx[2 * p]), (float)(c.x - sx[2 * p + 1]));
-                        const f32x2 Ay = pack2((float)(c.y - sy[2 * p]), (float)(c.y - sy[2 * p + 1]));
-                        const f32x2 Az = pack2((float)(c.z - sz[2 * p]), (float)(c.z - sz[2 * p + 1]));
-                        const f32x2 A2 = fma2(Az, Az, fma2(Ay, Ay, mul2(Ax, Ax)));
-                        const f32x2 yA = rsqrt2(A2);
-                        const f32x2 pa = mul2(qc2, yA);
-                        if (POT) {
-                            const f32x2 DA = fma2(Ax, T2x[p], fma2(Ay, T2y[p], fma2(Az, T2z[p], ND2[p])));
-                            const f32x2 R2 = sub2(A2, DA);
-                            const f32x2 yR = rsqrt2(R2);
-                            const f32x2 uA = mul2(yR, rcp2(fma2(A2, yA, mul2(R2, yR))));
-                            PA[p] = fma2(pa, mul2(DA, uA), PA[p]);
-                        }
-                        const f32x2 yA2 = mul2(yA, yA);
-                        const f32x2 meA = fma2(A2, yA2, mone2);
-                        const f32x2 zA = mul2(pa, yA2);
-                        const f32x2 wA = fma2(mul2(zA, meA), m15, zA);
-                        Fx[p] = fma2(wA, Ax, Fx[p]); Fy[p] = fma2(wA, Ay, Fy[p]); Fz[p] = fma2(wA, Az, Fz[p]);
-                    }
-                }
+                if (masked) diff_tile_N<NP, POT, true, UN>(shX, sx, sy, sz, lo, len, T2x, T2y, T2z, ND2, Fx, Fy, Fz, PA);
+                else diff_tile_N<NP, POT, false, UN>(shX, sx, sy, sz, lo, len, T2x, T2y, T2z, ND2, Fx, Fy, Fz, PA);
             }
             const f32x2 half2 = bcast2(0.5f);
-            bool bad = false;
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
                 unpack2(fma2(half2, Hx[p], Fx[p]), gx[2 * p], gx[2 * p + 1]);
@@ -272,13 +308,11 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
                 bad |= !(fabsf(gx[r]) + fabsf(gy[r]) + fabsf(gz[r]) < kc.big_f);
                 if (POT) bad |= !(fabsf(phc[r]) + fabsf(phs[r]) < kc.big_p);
             }
-            careful = __any_sync(0xffffffffu, bad);
-            if (careful) {
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) gx[r] = gy[r] = gz[r] = phc[r] = phs[r] = 0.f;
-            }
         }
-        if (careful) {
+        if (__any_sync(0xffffffffu, bad)) {
+            // some distance in this tile vanished: redo it pair by pair with the reference's rule (term dropped)
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) gx[r] = gy[r] = gz[r] = phc[r] = phs[r] = 0.f;
 #pragma unroll 1
             for (int j = 0; j < kTileCols; ++j) {
                 const int4 c = shX[j];
@@ -296,7 +330,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
             fx[r] += (double)gx[r]; fy[r] += (double)gy[r]; fz[r] += (double)gz[r];
-            if (POT) { pA[r] += (double)phc[r]; pC[r] += (double)phs[r]; }
+            if (POT) { pA[POT ? r : 0] += (double)phc[r]; pC[POT ? r : 0] += (double)phs[r]; }
         }
     }
 
@@ -310,8 +344,8 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
         const int lr = row_base + r * kBlock;
         if (lr < a.n_rows) {
             if (POT) {
-                out[0 * a.part_stride + lr] = pA[r] * s1;
-                out[1 * a.part_stride + lr] = pC[r] * s1;
+                out[0 * a.part_stride + lr] = pA[POT ? r : 0] * s1;
+                out[1 * a.part_stride + lr] = pC[POT ? r : 0] * s1;
             }
             out[2 * a.part_stride + lr] = fx[r] * s2;
             out[3 * a.part_stride + lr] = fy[r] * s2;
@@ -327,16 +361,48 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
 // (25.0 ms / 15.0 ms) although such an FFMA2 costs 4.0 cycles and two FFMAs 3.2 in isolation
 // (scripts/ubench.cu, profiles/r02_ubench.txt): the loop is bound by register-file operand reads, and
 // the scalar form adds issue slots without removing any.
-constexpr int kDiffRowsPot = 2, kDiffRowsField = 4;
 
-int diff_rows_per_block(bool with_pot) { return kBlock * (with_pot ? kDiffRowsPot : kDiffRowsField); }
+
+// UPOL_DIFF_VARIANT (sweeps only): other launch shapes / unroll factors of the same kernel
+static int diff_variant() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("UPOL_DIFF_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
+int diff_rows_per_block(bool with_pot) {
+    const int v = diff_variant();
+    if (with_pot) return kBlock * (v == 5 ? 4 : 2);
+    return kBlock * (v == 2 ? 2 : 4);
+}
+
+template <int ROWS, bool POT, int MINB, int UP, int UN>
+static void launch_diff(const PairArgs &a, cudaStream_t st) {
+    dim3 grid((unsigned)((a.n_rows + kBlock * ROWS - 1) / (kBlock * ROWS)), (unsigned)a.n_split);
+    pair_diff_kernel<ROWS, POT, MINB, UP, UN><<<grid, kBlock, 0, st>>>(a);
+}
 
 int launch_pair_diff(const PairArgs &a, bool with_pot, cudaStream_t st) {
     if (a.n_rows <= 0) return UPOL_OK;
-    const int rpb = diff_rows_per_block(with_pot);
-    dim3 grid((unsigned)((a.n_rows + rpb - 1) / rpb), (unsigned)a.n_split);
-    if (with_pot) pair_diff_kernel<kDiffRowsPot, true, 4><<<grid, kBlock, 0, st>>>(a);
-    else pair_diff_kernel<kDiffRowsField, false, 1><<<grid, kBlock, 0, st>>>(a);
+    const int v = diff_variant();
+    if (with_pot) {
+        switch (v) {
+            case 1: launch_diff<2, true, 3, 2, 4>(a, st); break;
+            case 2: launch_diff<2, true, 4, 1, 2>(a, st); break;
+            case 3: launch_diff<2, true, 4, 4, 4>(a, st); break;
+            case 4: launch_diff<2, true, 5, 2, 4>(a, st); break;
+            case 5: launch_diff<4, true, 3, 1, 2>(a, st); break;
+            default: launch_diff<2, true, 4, 2, 4>(a, st); break;
+        }
+    } else {
+        switch (v) {
+            case 1: launch_diff<4, false, 3, 1, 2>(a, st); break;
+            case 2: launch_diff<2, false, 4, 2, 4>(a, st); break;
+            case 3: launch_diff<4, false, 1, 1, 2>(a, st); break;
+            case 4: launch_diff<4, false, 2, 2, 4>(a, st); break;
+            default: launch_diff<4, false, 1, 2, 4>(a, st); break;
+        }
+    }
     UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
 }
