@@ -324,7 +324,10 @@ class Dist:
 
 
 def _e2e_energy_grad(D, sysm, s, d_host, precision_code, steps):
-    """The same step through the C ABI with page-locked HOST buffers: H2D of r and d, D2H of E and grad inside."""
+    """The same step through the C ABI with page-locked HOST buffers, copies inside the timed region: every rank
+    holds the full host arrays and calls upol_uind_energy_grad_host_sharded - its site slice of r and d goes up
+    (the peers' slices arrive over NVLink), the total energy and its slice of the gradient come down.  With one
+    rank the slice is everything.  Returns (ms, h2d bytes, d2h bytes summed over ranks, energy, assembled grad)."""
     from u_pol_b200 import _lib as L
 
     torch = D.torch
@@ -332,13 +335,13 @@ def _e2e_energy_grad(D, sysm, s, d_host, precision_code, steps):
     r_pin = torch.from_numpy(np.ascontiguousarray(s.r_core.reshape(-1))).pin_memory()
     d_pin = torch.from_numpy(np.ascontiguousarray(d_host.reshape(-1))).pin_memory()
     e_pin = torch.empty(L.E_SIZE, dtype=torch.float64).pin_memory()
-    g_pin = torch.empty(3 * n, dtype=torch.float64).pin_memory()
+    g_pin = torch.zeros(3 * n, dtype=torch.float64).pin_memory()
     r_host, d_flat, e_out, g_out = r_pin.numpy(), d_pin.numpy(), e_pin.numpy(), g_pin.numpy()
     lib = L.lib()
 
     def e2e_step():
-        L.check(lib.upol_system_set_positions(sysm._h, r_host.ctypes.data, None))
-        L.check(lib.upol_uind_energy_grad_host(sysm._h, d_flat.ctypes.data, precision_code, e_out.ctypes.data, g_out.ctypes.data))
+        L.check(lib.upol_uind_energy_grad_host_sharded(sysm._h, r_host.ctypes.data, d_flat.ctypes.data, precision_code,
+                                                       e_out.ctypes.data, g_out.ctypes.data, None, None))
 
     with torch.cuda.device(D.dev):
         for _ in range(2):
@@ -350,7 +353,8 @@ def _e2e_energy_grad(D, sysm, s, d_host, precision_code, steps):
             e2e_step()
         D.barrier()
         ms = D.max_over_ranks((time.perf_counter() - t0) / n_e2e * 1e3)
-    return ms, int(r_host.nbytes + d_flat.nbytes), int(g_out.nbytes + e_out.nbytes), e_out.copy(), g_out.copy()
+    # bytes moved by ALL ranks per step: the slices add up to the full arrays; every rank reads the energy vector
+    return ms, int(r_host.nbytes + d_flat.nbytes), int(g_out.nbytes + e_out.nbytes * D.world), e_out.copy(), g_out.copy()
 
 
 def _kernel_ms(sysm, fn, reps=5):
@@ -418,8 +422,12 @@ def run_energy_grad(args):
     e_host, g_dev = e.cpu().numpy(), g
     value = pairs_per_step / (ms_per_step * 1e-3)
     k64_ms, k64_n = _kernel_ms(sysm, step64)
-    e2e_ms, h2d, d2h, e_out, _ = _e2e_energy_grad(D, sysm, s, d_host, L.FP64, args.steps)
+    e2e_ms, h2d, d2h, e_out, g_e2e = _e2e_energy_grad(D, sysm, s, d_host, L.FP64, args.steps)
     assert abs(e_out[0] - e_host[0]) <= 1e-9 * abs(e_host[0]), (e_out[0], e_host[0])
+    # the host path returns this rank's gradient rows only: they must be the rows of the device-resident result
+    g_ref_host = g_dev.cpu().numpy().reshape(-1)
+    nz = g_e2e != 0
+    assert nz.any() and float(np.abs(g_e2e[nz] - g_ref_host[nz]).max()) <= 1e-9 * float(np.abs(g_ref_host).max())
 
     # ---- the same step in mixed precision (one fp32 difference-form pass) -----------------------
     mx_ms, _, _ = D.timed_steps(stepmx, args.steps, warmup)

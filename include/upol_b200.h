@@ -131,6 +131,21 @@ int upol_uind_energy_grad_host(upol_system *sys, const double *d, int precision,
                                double *energy, double *grad);
 
 /*
+ * Sharded host path for row-sharded runs (after upol_system_attach_comm; every rank calls it with the same
+ * arguments' meaning).  Each rank holds the full host arrays but moves only ITS site slice across PCIe:
+ *   r_core[nsite*3]  new geometry, or NULL to keep the current one; only [site_lo, site_hi) is uploaded and the
+ *                    peers' slices arrive over NVLink (peer stores after upol_system_p2p_attach, NCCL otherwise)
+ *   d[nsite*3]       same rule
+ *   energy[UPOL_E_SIZE]  the TOTAL over all ranks, identical bits on every rank (may be NULL)
+ *   grad[nsite*3]    only the entries [3*site_lo, 3*site_hi) are written - the rows this rank evaluated; the
+ *                    caller (or rank 0) assembles the slices.  May be NULL.
+ *   site_lo/site_hi  out (may be NULL): the rank's site range (its molecule block)
+ * With one rank it is upol_system_set_positions + upol_uind_energy_grad_host in one call.
+ */
+int upol_uind_energy_grad_host_sharded(upol_system *sys, const double *r_core, const double *d, int precision,
+                                       double *energy, double *grad, int64_t *site_lo, int64_t *site_hi);
+
+/*
  * dUind/dr_core at fixed displacements, dudr[nsite*3] (kJ mol^-1 nm^-1); the force on core i is
  * -dudr[i].  NEW relative to the reference (SURVEY 8f "next" #3): U_pol has no such function; it
  * is what an MD driver needs to move the cores on the U_ind surface.  fp64.  Sharded runs compute the
@@ -198,21 +213,22 @@ int upol_minimize_host(upol_system *sys, double *d, const upol_min_options *opts
  * (torch.distributed in the Python host layer) and attaches the communicator to the system.
  * After that, energy/gradient calls all-reduce the energy vector and all-gather the gradient,
  * and the minimiser performs one all-gather of d and one all-reduce of a scalar pack per
- * iteration.
+ * iteration - through NCCL, or without any NCCL call once the peer mapping below is in place.
  */
 #define UPOL_COMM_ID_BYTES 128
 int upol_comm_unique_id(unsigned char *id_bytes);
 int upol_system_attach_comm(upol_system *sys, const unsigned char *id_bytes, int rank, int nranks);
 
 /*
- * Peer-memory exchange for the minimiser loop (optional, after upol_system_attach_comm).  Each rank
- * exports CUDA-IPC handles of its displacement vector, its scalar-pack mailbox and its arrival
- * flags (UPOL_P2P_EXPORT_BYTES), the caller all-gathers the blobs (rank order) and hands them back.
- * From then on a minimiser iteration uses no NCCL call: the update kernel stores its slice of d
- * straight into every peer's vector over NVLink and raises the peers' arrival flags; the partial
- * inner products travel the same way and every rank sums them in rank order (deterministic).
+ * Peer-memory exchange (optional, after upol_system_attach_comm).  Each rank exports CUDA-IPC handles of its
+ * exchange buffers (displacements, gradient rows, positions, mailboxes, arrival flags: UPOL_P2P_EXPORT_BYTES),
+ * the caller all-gathers the blobs (rank order) and hands them back.  From then on neither a minimiser iteration
+ * nor an energy/gradient call uses NCCL: the minimiser's update kernel stores its slice of d straight into every
+ * peer's vector over NVLink and raises the peers' arrival flags, the partial inner products travel the same way;
+ * the finalize kernel of an evaluation stores its gradient rows and the rank's energy partials into every peer
+ * (fused compute + all-gather); sums are taken in rank order, so every rank holds the same bits.
  */
-#define UPOL_P2P_EXPORT_BYTES 192
+#define UPOL_P2P_EXPORT_BYTES 512
 int upol_system_p2p_export(upol_system *sys, unsigned char *blob);
 int upol_system_p2p_attach(upol_system *sys, const unsigned char *all_blobs);
 /* Back to NCCL for the minimiser loop (every rank must call it, e.g. when a peer could not map). */

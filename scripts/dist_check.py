@@ -30,6 +30,22 @@ dd = float((d2 - d1).abs().max())
 print(f"rank {rank}/{world}: dE {rel_e:.2e} dg {rel_g:.2e} dUmin {rel_m:.2e} dd {dd:.2e} iters {i1['iterations']}/{i2['iterations']} "
       f"evals {i1['evaluations']}/{i2['evaluations']} t_full {t_full:.3f}s t_sharded {t_sh:.3f}s", flush=True)
 assert rel_e < 1e-11 and rel_g < 1e-12 and rel_m < 1e-10, "sharded result differs"
+# energy-only and gradient-only calls, repeated (epoch parity of the peer-memory exchange), then the sharded host path
+for rep in range(3):
+    e3, _ = sh.energy_grad(D, want_grad=False)
+    _, g3 = sh.energy_grad(D, want_energy=False)
+    assert abs(float(e3[0]) - float(e1[0])) <= 1e-11 * abs(float(e1[0])) and float((g3 - g1).abs().max() / g1.abs().max()) < 1e-12
+em, gm = sh.energy_grad(D, precision="mixed")
+assert abs(float(em[0]) - float(e1[0])) <= 1e-5 * abs(float(e1[0])) and float((gm - g1).abs().max() / g1.abs().max()) < 1e-5
+r_host = np.ascontiguousarray(s.r_core.reshape(-1)); d_host = np.ascontiguousarray(np.asarray(D).reshape(-1))
+for rep in range(3):
+    eh, gh, (slo, shi) = sh.energy_grad_host_sharded(d_host, r_core=r_host if rep != 1 else None)
+    gt = torch.as_tensor(gh).to(g1.device)
+    dist.all_reduce(gt)                       # the caller assembles the slices (zeros elsewhere)
+    assert abs(eh[0] - float(e1[0])) <= 1e-11 * abs(float(e1[0])), (eh[0], float(e1[0]))
+    assert float((gt - g1).abs().max() / g1.abs().max()) < 1e-12
+    assert np.all(gh[:slo] == 0) and np.all(gh[shi:] == 0)
+print(f"rank {rank}: peer-memory energy/gradient exchange and sharded host path ok (sites {slo}:{shi})", flush=True)
 cg1 = full.core_gradient(D); cg2 = sh.core_gradient(D)
 rel_c = float((cg1 - cg2).abs().max() / cg1.abs().max())
 assert rel_c < 1e-10, rel_c

@@ -20,6 +20,17 @@ def test_two_rank_nccl_matches_single_gpu():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("dE ") == 2 and out.stdout.count("batched replicas ok") == 2 and out.stdout.count("sharded core gradient ok") == 2
+    assert out.stdout.count("sharded host path ok") == 2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_two_rank_nccl_only_matches_single_gpu():
+    """The same check with the peer mapping switched off: NCCL all-reduce / all-gather everywhere."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29545", os.path.join(ROOT, "scripts", "dist_check.py"), "600"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, UPOL_NO_P2P="1"))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("sharded host path ok") == 2
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")

@@ -17,7 +17,7 @@ FP64, MIXED = 0, 1
 LBFGS, CG = 0, 1
 FLAG_NOT_CONVERGED, FLAG_NONFINITE, FLAG_LINESEARCH, FLAG_COMM = 1, 2, 4, 8
 COMM_ID_BYTES = 128
-P2P_EXPORT_BYTES = 192
+P2P_EXPORT_BYTES = 512
 
 
 class MinOptions(C.Structure):
@@ -52,6 +52,7 @@ _SIGNATURES = {
     "upol_system_set_row_range": (C.c_int, [_P, _I64, _I64]),
     "upol_uind_energy_grad_dev": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "upol_uind_energy_grad_host": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "upol_uind_energy_grad_host_sharded": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.POINTER(_I64), C.POINTER(_I64)]),
     "upol_uind_core_gradient_dev": (C.c_int, [_P, _P, _P, _P]),
     "upol_coulomb_static_dev": (C.c_int, [_P, _P, _P]),
     "upol_uself_dev": (C.c_int, [_P, _P, _I64, _P, _P]),

@@ -280,25 +280,22 @@ int upol_system_set_positions(upol_system *s, const double *r_core, void *stream
     if (!s || !r_core) return UPOL_ERR_ARG;
     DeviceGuard guard(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    compute_centre(s, r_core);
     // stage through pinned memory so the copy is a true async DMA; the caller's buffer is free on return
     const size_t n3 = 3 * (size_t)s->nsite;
     int rc = sys_ensure_pinned(s, sizeof(double) * (2 * n3 + UPOL_E_SIZE));
     if (rc) return rc;
-    if (is_pinned(r_core)) {                              // page-locked caller buffer: copy straight from it
-        UPOL_CUDA(cudaMemcpyAsync(s->r, r_core, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
-        rc = sys_upload_positions(s, nullptr, st);
-        if (rc) return rc;
-        UPOL_CUDA(cudaStreamSynchronize(st));             // the caller may reuse its buffer on return
-        return UPOL_OK;
+    const double *src = r_core;
+    if (!is_pinned(r_core)) {                             // page-locked caller buffers are copied from directly
+        UPOL_CUDA(cudaStreamSynchronize(st));             // staging buffer may still be in flight
+        memcpy(s->pin, r_core, sizeof(double) * n3);
+        src = s->pin;
     }
-    UPOL_CUDA(cudaStreamSynchronize(st));                 // staging buffer may still be in flight
-    memcpy(s->pin, r_core, sizeof(double) * n3);
-    UPOL_CUDA(cudaMemcpyAsync(s->r, s->pin, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
-    rc = sys_upload_positions(s, nullptr, st);
+    UPOL_CUDA(cudaMemcpyAsync(s->r, src, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
+    // box centre / fixed-point grid from the device copy (one block, 6 doubles back) instead of a host loop over
+    // all sites; the synchronisation inside also makes the caller's / the staging buffer reusable on return
+    rc = sys_box_from_device(s, st);
     if (rc) return rc;
-    UPOL_CUDA(cudaStreamSynchronize(st));                 // pin is reused by the *_host entry points
-    return UPOL_OK;
+    return sys_upload_positions(s, nullptr, st);
 }
 
 int upol_system_set_positions_dev(upol_system *s, const double *r_core_dev, void *stream) {
@@ -354,13 +351,77 @@ int upol_uind_energy_grad_dev(upol_system *s, const double *d, int precision, do
     o.want_grad = grad != nullptr;
     o.want_energy = energy != nullptr;      // NULL: field pass only (what a minimiser iteration needs)
     o.d_full = d;                           // gathered into s->dc by the prepare kernel
-    int rc = sys_eval_compact(s, s->dc, o, energy, s->gc, st);
+    // Sharded runs with the peer mapping in place: the finalize kernel stores its gradient rows and the rank's
+    // energy partials into every peer (fused compute + all-gather / all-reduce over NVLink), no NCCL call
+    const bool px = s->p2p && s->nranks > 1;
+    double *gbuf = s->gc;
+    if (px) { o.gx = make_eval_xchg(s, grad != nullptr); gbuf = s->xg + o.gx.g_off; }
+    int rc = sys_eval_compact(s, s->dc, o, energy, gbuf, st);
     if (rc) return rc;
     if (grad) {
-        if (s->nranks > 1) { rc = comm_allgather_rows(s, s->gc, st); if (rc) return rc; }
-        rc = sys_scatter_g(s, s->gc, grad, st);
+        if (s->nranks > 1 && !px) { rc = comm_allgather_rows(s, gbuf, st); if (rc) return rc; }
+        rc = sys_scatter_g(s, gbuf, grad, st);
     }
     return rc;
+}
+
+// Sharded host path: see the header.
+static int upol_uind_energy_grad_host_sharded_impl(upol_system *s, const double *r_core, const double *d, int precision,
+                                                   double *energy, double *grad, int64_t *site_lo_out, int64_t *site_hi_out) {
+    if (!s || !d || (!energy && !grad)) return UPOL_ERR_ARG;
+    DeviceGuard guard(s->device);
+    int64_t lo = 0, hi = s->nsite;
+    int rc = comm_site_range(s, s->rank, &lo, &hi);
+    if (rc) return rc;
+    if (site_lo_out) *site_lo_out = lo;
+    if (site_hi_out) *site_hi_out = hi;
+    const size_t n3 = 3 * (size_t)s->nsite, m3 = 3 * (size_t)(hi - lo), o3 = 3 * (size_t)lo;
+    rc = sys_ensure_pinned(s, sizeof(double) * (2 * n3 + UPOL_E_SIZE));
+    if (rc) return rc;
+    rc = sys_ensure_hscratch(s, 2 * n3 + UPOL_E_SIZE);
+    if (rc) return rc;
+    if (!s->xd) UPOL_CUDA(cudaMalloc((void **)&s->xd, sizeof(double) * n3));      // single rank / NCCL-only runs
+    double *gfull = s->hscratch + n3, *e_dev = gfull + n3;
+    double *pr = s->pin, *pd = s->pin + m3, *pg = s->pin + 2 * m3, *pe = s->pin + 2 * n3;
+    cudaStream_t st = 0;
+    // only this rank's site slices of r and d cross PCIe; the peers' slices arrive over NVLink
+    if (r_core) {
+        const double *src = r_core + o3;
+        if (!is_pinned(r_core)) { memcpy(pr, src, sizeof(double) * m3); src = pr; }
+        if (m3) UPOL_CUDA(cudaMemcpyAsync(s->r + o3, src, sizeof(double) * m3, cudaMemcpyHostToDevice, st));
+    }
+    {
+        const double *src = d + o3;
+        if (!is_pinned(d)) { memcpy(pd, src, sizeof(double) * m3); src = pd; }
+        if (m3) UPOL_CUDA(cudaMemcpyAsync(s->xd + o3, src, sizeof(double) * m3, cudaMemcpyHostToDevice, st));
+    }
+    rc = p2p_allgather_r_d(s, r_core != nullptr, st);
+    if (rc) return rc;
+    if (r_core) {
+        rc = sys_box_from_device(s, st);
+        if (rc) return rc;
+        rc = sys_upload_positions(s, nullptr, st);
+        if (rc) return rc;
+    }
+    EvalOpts o;
+    o.precision = precision;
+    o.want_grad = grad != nullptr;
+    o.want_energy = energy != nullptr;
+    o.d_full = s->xd;
+    if (s->p2p && s->nranks > 1) o.gx = make_eval_xchg(s, false);     // energy partials only: every rank keeps its rows
+    rc = sys_eval_compact(s, s->dc, o, e_dev, s->gc, st);
+    if (rc) return rc;
+    const bool e_pin = energy && is_pinned(energy), g_pin = grad && is_pinned(grad);
+    if (energy) UPOL_CUDA(cudaMemcpyAsync(e_pin ? energy : pe, e_dev, sizeof(double) * UPOL_E_SIZE, cudaMemcpyDeviceToHost, st));
+    if (grad && m3) {
+        rc = sys_scatter_g_range(s, s->gc, gfull, lo, hi, st);
+        if (rc) return rc;
+        UPOL_CUDA(cudaMemcpyAsync(g_pin ? grad + o3 : pg, gfull + o3, sizeof(double) * m3, cudaMemcpyDeviceToHost, st));
+    }
+    UPOL_CUDA(cudaStreamSynchronize(st));
+    if (energy && !e_pin) memcpy(energy, pe, sizeof(double) * UPOL_E_SIZE);
+    if (grad && !g_pin && m3) memcpy(grad + o3, pg, sizeof(double) * m3);
+    return UPOL_OK;
 }
 
 int upol_uind_energy_grad_host(upol_system *s, const double *d, int precision, double *energy, double *grad) {
@@ -495,6 +556,17 @@ int upol_minimize_host(upol_system *s, double *d, const upol_min_options *opts, 
     UPOL_CUDA(cudaStreamSynchronize(0));
     memcpy(d, s->pin, sizeof(double) * n3);
     return rc;
+}
+
+int upol_uind_energy_grad_host_sharded(upol_system *s, const double *r_core, const double *d, int precision,
+                                       double *energy, double *grad, int64_t *site_lo, int64_t *site_hi) {
+    try {
+        return upol_uind_energy_grad_host_sharded_impl(s, r_core, d, precision, energy, grad, site_lo, site_hi);
+    } catch (const std::bad_alloc &) {
+        return UPOL_ERR_ALLOC;
+    } catch (...) {
+        return UPOL_ERR_ARG;
+    }
 }
 
 // C ABI: no C++ exception may cross the boundary

@@ -8,6 +8,7 @@
 // CPU-only host for the symbol checks.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -119,11 +120,93 @@ int comm_allgather_sites(upol_system *s, double *vec3, cudaStream_t st) {
 void p2p_destroy(upol_system *s) {
     for (void *p : s->ipc_opened) cudaIpcCloseMemHandle(p);
     s->ipc_opened.clear();
-    void *ptrs[] = {s->xchg_pack, s->xchg_flags, s->d_peer_x, s->d_peer_pack, s->d_peer_flags};
+    void *ptrs[] = {s->xchg_pack, s->xchg_flags, s->d_peer_x, s->d_peer_pack, s->d_peer_flags,
+                    s->xg, s->xe, s->xd, s->xflags2, s->d_peer_g, s->d_peer_e, s->d_peer_r, s->d_peer_d, s->d_peer_flags2};
     for (void *p : ptrs) if (p) cudaFree(p);
     s->xchg_pack = nullptr; s->xchg_flags = nullptr;
     s->d_peer_x = nullptr; s->d_peer_pack = nullptr; s->d_peer_flags = nullptr;
+    s->xg = nullptr; s->xe = nullptr; s->xd = nullptr; s->xflags2 = nullptr;
+    s->d_peer_g = nullptr; s->d_peer_e = nullptr; s->d_peer_r = nullptr; s->d_peer_d = nullptr; s->d_peer_flags2 = nullptr;
     s->p2p = false;
+}
+
+int comm_site_range(const upol_system *s, int rank, int64_t *site_lo, int64_t *site_hi) {
+    if (s->nranks <= 1) { *site_lo = 0; *site_hi = s->nsite; return UPOL_OK; }
+    const CommState *c = static_cast<const CommState *>(s->comm);
+    if (!c || rank < 0 || rank >= s->nranks) return UPOL_ERR_ARG;
+    *site_lo = c->site_lo[rank]; *site_hi = c->site_hi[rank];
+    return UPOL_OK;
+}
+
+namespace {
+
+constexpr int kNumIpc = 8;   // handles a rank exports: dc, xchg_pack, xchg_flags, xg, xe, xd, r, xflags2
+
+// All-gather by peer stores of the rank's site slice [e0, e1) (in doubles) of r (optional) and of the (nsite,3)
+// displacements: every element goes to the same offset of every peer's array; the block that finishes last
+// raises the rank's arrival epoch (flag slot 1) on every peer.
+__global__ void __launch_bounds__(256)
+push_slices_kernel(int64_t e0, int64_t e1, int with_r, const double *__restrict__ r, const double *__restrict__ d,
+                   double **peer_r, double **peer_d, int **peer_flags, int *my_flags, int rank, int nranks, int epoch) {
+    for (int64_t e = e0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += (int64_t)gridDim.x * blockDim.x) {
+        const double dv = d[e];
+        const double rv = with_r ? r[e] : 0.0;
+        for (int g = 0; g < nranks; ++g) {
+            if (g == rank) continue;
+            peer_d[g][e] = dv;
+            if (with_r) peer_r[g][e] = rv;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int last;
+    int *ticket = my_flags + 3 * nranks;
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) *ticket = 0;
+        __threadfence_system();
+        if ((int)threadIdx.x < nranks && (int)threadIdx.x != rank)
+            *((volatile int *)(peer_flags[threadIdx.x] + nranks + rank)) = epoch;
+    }
+}
+
+__global__ void wait_slices_kernel(const int *my_flags, int rank, int nranks, int epoch, double *poison) {
+    bool ok = true;
+    if ((int)threadIdx.x < nranks && (int)threadIdx.x != rank) {
+        const volatile int *f = my_flags + nranks + threadIdx.x;
+        const long long t0 = clock64();
+        while (*f < epoch) {
+            if (clock64() - t0 > 60000000000LL) { ok = false; break; }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    // a dead peer must not pass silently: its slice of d becomes NaN, and so does everything computed from it
+    if (!ok && poison != nullptr) poison[0] = nan("");
+}
+
+}  // namespace
+
+int p2p_allgather_r_d(upol_system *s, bool with_r, cudaStream_t st) {
+    if (s->nranks <= 1) return UPOL_OK;
+    if (!s->p2p) {
+        int rc = with_r ? comm_allgather_sites(s, s->r, st) : UPOL_OK;
+        if (rc) return rc;
+        return comm_allgather_sites(s, s->xd, st);
+    }
+    int64_t lo = 0, hi = 0;
+    int rc = comm_site_range(s, s->rank, &lo, &hi);
+    if (rc) return rc;
+    const int epoch = ++s->epoch_push;
+    const int64_t n = 3 * (hi - lo);
+    const unsigned nb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(148 * 4, (n + 255) / 256));
+    push_slices_kernel<<<nb, 256, 0, st>>>(3 * lo, 3 * hi, with_r ? 1 : 0, s->r, s->xd, s->d_peer_r, s->d_peer_d,
+                                           s->d_peer_flags2, s->xflags2, s->rank, s->nranks, epoch);
+    wait_slices_kernel<<<1, 32, 0, st>>>(s->xflags2, s->rank, s->nranks, epoch, s->xd);
+    s->launches += 2;
+    UPOL_CUDA(cudaGetLastError());
+    return UPOL_OK;
 }
 
 void comm_destroy(upol_system *s) {
@@ -194,21 +277,30 @@ extern "C" int upol_system_p2p_export(upol_system *s, unsigned char *blob) {
     cudaGetDevice(&prev);
     cudaSetDevice(s->device);
     p2p_destroy(s);
-    const size_t nflag = 2 * (size_t)s->nranks + 1;
+    const size_t nflag = 2 * (size_t)s->nranks + 1, nflag2 = 3 * (size_t)s->nranks + 4;
+    const size_t ng = 2 * 3 * (size_t)std::max<int64_t>(s->nd, 1), ne = 2 * (size_t)s->nranks * UPOL_E_SIZE;
+    const size_t nx = 3 * (size_t)s->nsite;
     cudaError_t e = cudaMalloc((void **)&s->xchg_pack, sizeof(double) * (size_t)s->nranks * kMaxPack);
     if (e == cudaSuccess) e = cudaMalloc((void **)&s->xchg_flags, sizeof(int) * nflag);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->xg, sizeof(double) * ng);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->xe, sizeof(double) * ne);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->xd, sizeof(double) * nx);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&s->xflags2, sizeof(int) * nflag2);
     if (e == cudaSuccess) e = cudaMemset(s->xchg_pack, 0, sizeof(double) * (size_t)s->nranks * kMaxPack);
     if (e == cudaSuccess) e = cudaMemset(s->xchg_flags, 0, sizeof(int) * nflag);
-    cudaIpcMemHandle_t h[3];
-    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[0], s->dc);
-    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[1], s->xchg_pack);
-    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h[2], s->xchg_flags);
+    if (e == cudaSuccess) e = cudaMemset(s->xg, 0, sizeof(double) * ng);
+    if (e == cudaSuccess) e = cudaMemset(s->xe, 0, sizeof(double) * ne);
+    if (e == cudaSuccess) e = cudaMemset(s->xd, 0, sizeof(double) * nx);
+    if (e == cudaSuccess) e = cudaMemset(s->xflags2, 0, sizeof(int) * nflag2);
+    cudaIpcMemHandle_t h[kNumIpc];
+    void *exported[kNumIpc] = {s->dc, s->xchg_pack, s->xchg_flags, s->xg, s->xe, s->xd, s->r, s->xflags2};
+    for (int k = 0; k < kNumIpc && e == cudaSuccess; ++k) e = cudaIpcGetMemHandle(&h[k], exported[k]);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (prev >= 0) cudaSetDevice(prev);
     if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
-    static_assert(3 * sizeof(cudaIpcMemHandle_t) == UPOL_P2P_EXPORT_BYTES, "blob size");
+    static_assert(kNumIpc * sizeof(cudaIpcMemHandle_t) == UPOL_P2P_EXPORT_BYTES, "blob size");
     memcpy(blob, h, sizeof(h));
-    s->p2p_epoch = 0;
+    s->p2p_epoch = 0; s->epoch_eval = 0; s->epoch_push = 0;
     return UPOL_OK;
 }
 
@@ -218,26 +310,27 @@ extern "C" int upol_system_p2p_attach(upol_system *s, const unsigned char *all) 
     cudaGetDevice(&prev);
     cudaSetDevice(s->device);
     const int nr = s->nranks;
-    std::vector<double *> px(nr), pp(nr);
-    std::vector<int *> pf(nr);
+    // tab[k][r]: rank r's k-th exported buffer as seen from this device (own buffers for r = rank)
+    std::vector<std::vector<void *>> tab(kNumIpc, std::vector<void *>(nr, nullptr));
+    void *own[kNumIpc] = {s->dc, s->xchg_pack, s->xchg_flags, s->xg, s->xe, s->xd, s->r, s->xflags2};
     cudaError_t e = cudaSuccess;
     for (int r = 0; r < nr && e == cudaSuccess; ++r) {
-        if (r == s->rank) { px[r] = s->dc; pp[r] = s->xchg_pack; pf[r] = s->xchg_flags; continue; }
-        cudaIpcMemHandle_t h[3];
+        if (r == s->rank) { for (int k = 0; k < kNumIpc; ++k) tab[k][r] = own[k]; continue; }
+        cudaIpcMemHandle_t h[kNumIpc];
         memcpy(h, all + (size_t)r * UPOL_P2P_EXPORT_BYTES, sizeof(h));
-        void *q[3] = {nullptr, nullptr, nullptr};
-        for (int k = 0; k < 3 && e == cudaSuccess; ++k) {
-            e = cudaIpcOpenMemHandle(&q[k], h[k], cudaIpcMemLazyEnablePeerAccess);
-            if (e == cudaSuccess) s->ipc_opened.push_back(q[k]);
+        for (int k = 0; k < kNumIpc && e == cudaSuccess; ++k) {
+            void *q = nullptr;
+            e = cudaIpcOpenMemHandle(&q, h[k], cudaIpcMemLazyEnablePeerAccess);
+            if (e == cudaSuccess) s->ipc_opened.push_back(q);
+            tab[k][r] = q;
         }
-        px[r] = (double *)q[0]; pp[r] = (double *)q[1]; pf[r] = (int *)q[2];
     }
-    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_peer_x, sizeof(double *) * nr);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_peer_pack, sizeof(double *) * nr);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&s->d_peer_flags, sizeof(int *) * nr);
-    if (e == cudaSuccess) e = cudaMemcpy(s->d_peer_x, px.data(), sizeof(double *) * nr, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(s->d_peer_pack, pp.data(), sizeof(double *) * nr, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(s->d_peer_flags, pf.data(), sizeof(int *) * nr, cudaMemcpyHostToDevice);
+    void **dst[kNumIpc] = {(void **)&s->d_peer_x, (void **)&s->d_peer_pack, (void **)&s->d_peer_flags, (void **)&s->d_peer_g,
+                           (void **)&s->d_peer_e, (void **)&s->d_peer_d, (void **)&s->d_peer_r, (void **)&s->d_peer_flags2};
+    for (int k = 0; k < kNumIpc && e == cudaSuccess; ++k) {
+        e = cudaMalloc(dst[k], sizeof(void *) * nr);
+        if (e == cudaSuccess) e = cudaMemcpy(*dst[k], tab[k].data(), sizeof(void *) * nr, cudaMemcpyHostToDevice);
+    }
     if (prev >= 0) cudaSetDevice(prev);
     if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); p2p_destroy(s); return UPOL_ERR_CUDA; }
     s->p2p = true;

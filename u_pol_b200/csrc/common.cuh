@@ -70,6 +70,20 @@ struct PairArgs {
     int gate_skip_mask;
 };
 
+// Peer-memory exchange of one evaluation (multi-GPU, after upol_system_p2p_attach): finalize_rows_kernel stores
+// the gradient rows of its shard and the rank's energy partials straight into every peer (NVLink stores), fences,
+// and its last block raises the rank's arrival epoch on every peer; eval_xchg_wait_kernel waits for all epochs and
+// adds the energy partials in rank order (every rank gets the same bits).  No NCCL call, no separate all-gather.
+struct EvalXchg {
+    int on, rank, nranks, epoch;
+    int push_grad;          // 0: only the energy partials travel (sharded host path: every rank keeps its own rows)
+    double **peer_g;        // every rank's xg (self included)
+    double **peer_e;        // every rank's xe
+    int **peer_flags;       // every rank's xflags2
+    int64_t g_off;          // (epoch & 1) * 3 * nd
+    int e_off;              // (epoch & 1) * nranks * UPOL_E_SIZE
+};
+
 // gate bits written by the minimiser's control kernel
 constexpr int kGateDone = 1, kGatePhase64 = 2, kGatePhaseMixed = 4;
 constexpr int kMaxPack = 17 * 8;   // (max history + 1) x values per slot of the minimiser's scalar pack
@@ -167,6 +181,15 @@ struct upol_system {
     int **d_peer_flags = nullptr;     // device table [nranks]: peers' xchg_flags
     std::vector<void *> ipc_opened;   // mapped peer pointers (closed at destroy)
     int p2p_epoch = 0;                // last epoch handed out (monotonic across minimisations)
+    // the same for the energy/gradient entry points and the sharded host path: finalize_rows_kernel stores its
+    // gradient rows and the rank's energy partials into every peer, push_slices_kernel the rank's slices of r and d
+    double *xg = nullptr;             // [2][3*nd] gradient rows of all ranks, double-buffered by epoch parity
+    double *xe = nullptr;             // [2][nranks][UPOL_E_SIZE] energy partials of every rank, same parity rule
+    double *xd = nullptr;             // [3*nsite] displacements in the (nsite,3) layout (sharded host path)
+    int *xflags2 = nullptr;           // [3][nranks] arrival epochs (evaluation results | r slices | d slices) + [4] block counters
+    double **d_peer_g = nullptr, **d_peer_e = nullptr, **d_peer_r = nullptr, **d_peer_d = nullptr;   // device tables [nranks]
+    int **d_peer_flags2 = nullptr;
+    int epoch_eval = 0, epoch_push = 0;
 
     // minimiser workspace (allocated on first use)
     void *min_ws = nullptr;
@@ -192,12 +215,15 @@ struct EvalOpts {
     const int *gate = nullptr;     // minimiser gate word (see kGate*)
     bool phase_switch = false;     // minimiser: launch both field kernels, gate picks one
     const double *d_full = nullptr; // displacements in the (nsite,3) layout: gathered into s->dc by the prepare kernel
+    EvalXchg gx = {0, 0, 1, 0, 0, nullptr, nullptr, nullptr, 0, 0};   // peer-memory exchange instead of NCCL (reduce_ranks)
 };
+EvalXchg make_eval_xchg(upol_system *s, bool push_grad);   // hands out the next evaluation epoch
 int sys_eval_compact(upol_system *s, const double *d_compact, const EvalOpts &o,
                      double *energy_dev, double *grad_compact, cudaStream_t st);
 int sys_static_part(upol_system *s, cudaStream_t st);
 int sys_gather_d(upol_system *s, const double *d_full, double *d_compact, cudaStream_t st);
 int sys_scatter_g(upol_system *s, const double *g_compact, double *g_full, cudaStream_t st);
+int sys_scatter_g_range(upol_system *s, const double *g_compact, double *g_full, int64_t site_lo, int64_t site_hi, cudaStream_t st);
 int sys_scatter_d(upol_system *s, const double *d_compact, double *d_full, cudaStream_t st);
 int sys_ensure_pinned(upol_system *s, size_t bytes);
 int sys_ensure_hscratch(upol_system *s, size_t elems);
@@ -215,6 +241,8 @@ const char *last_error_message();
 int comm_allreduce_sum(upol_system *s, double *buf, int64_t n, cudaStream_t st);
 int comm_allgather_rows(upol_system *s, double *vec3, cudaStream_t st);  // [nd*3] in place by shard
 int comm_allgather_sites(upol_system *s, double *vec3, cudaStream_t st); // [nsite*3] in place by shard
+int comm_site_range(const upol_system *s, int rank, int64_t *site_lo, int64_t *site_hi);
+int p2p_allgather_r_d(upol_system *s, bool with_r, cudaStream_t st);     // site slices of s->r and s->xd by peer stores
 void comm_destroy(upol_system *s);
 void p2p_destroy(upol_system *s);
 

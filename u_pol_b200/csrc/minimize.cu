@@ -41,7 +41,7 @@ constexpr int kDotVals = 8;          // per history slot: 4 used; last row: 6 us
 constexpr int kMaxLineSearch = 12;
 
 // integer control words
-enum { I_GATE = 0, I_ITER, I_NEVAL, I_HCOUNT, I_HHEAD, I_LS, I_FLAGS, I_ACCEPT, I_FIRST, I_NEWSLOT, I_PUSHED, I_SIZE = 16 };
+enum { I_GATE = 0, I_ITER, I_NEVAL, I_HCOUNT, I_HHEAD, I_LS, I_FLAGS, I_ACCEPT, I_FIRST, I_NEWSLOT, I_PUSHED, I_MAXITER, I_TICKET, I_SIZE = 16 };
 // double control words
 enum { D_ALPHA = 0, D_ALPHA_PREV, D_PHI0, D_ALO, D_DLO, D_AHI, D_DHI, D_GAMMA, D_GNORM, D_GNORM0, D_TOL, D_SWITCH, D_SIZE = 16 };
 
@@ -67,6 +67,12 @@ struct MinWs {
     double *h_sc = nullptr;                  // pinned
     double *e_final = nullptr;               // [UPOL_E_SIZE]
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // single-rank fast path: a chunk of `check_every` slots captured once into a CUDA graph and replayed
+    cudaStream_t gstream = nullptr;          // capture needs a non-legacy stream
+    cudaEvent_t gev[2] = {nullptr, nullptr};
+    cudaGraphExec_t gexec = nullptr;
+    long long gkey[6] = {-1, -1, -1, -1, -1, -1};   // (m, mixed, check_every, row_lo, row_hi, geometry-independent launch shape)
+    bool graph_failed = false;
 };
 
 void ws_free(MinWs *w) {
@@ -77,6 +83,9 @@ void ws_free(MinWs *w) {
     if (w->h_ic) cudaFreeHost(w->h_ic);
     if (w->h_sc) cudaFreeHost(w->h_sc);
     for (auto &e : w->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : w->gev) if (e) cudaEventDestroy(e);
+    if (w->gexec) cudaGraphExecDestroy(w->gexec);
+    if (w->gstream) cudaStreamDestroy(w->gstream);
     delete w;
 }
 
@@ -191,9 +200,10 @@ __global__ void wait_x_kernel(int *ic, P2P pp, int epoch_prev) {
     if (!__all_sync(0xffffffffu, ok) && threadIdx.x == 0) { ic[I_FLAGS] |= UPOL_FLAG_COMM; ic[I_GATE] |= kGateDone; }
 }
 
-__global__ void init_state_kernel(int *ic, double *sc, double tol, int phase_bits) {
+__global__ void init_state_kernel(int *ic, double *sc, double tol, int phase_bits, int maxiter) {
     if (threadIdx.x || blockIdx.x) return;
     for (int i = 0; i < I_SIZE; ++i) ic[i] = 0;
+    ic[I_MAXITER] = maxiter;
     for (int i = 0; i < D_SIZE; ++i) sc[i] = 0.0;
     ic[I_GATE] = phase_bits;
     ic[I_FIRST] = 1;
@@ -273,38 +283,10 @@ dots_reduce_kernel(int m, int nblocks, const int *__restrict__ ic, const double 
 }
 
 // Single-thread controller: line-search decision, history bookkeeping, m x m solves.
-__global__ void __launch_bounds__(kMaxPack + 24)
-control_kernel(int m, int maxiter, int mixed_enabled, int *__restrict__ ic, double *__restrict__ sc,
-               double *__restrict__ pack, double *__restrict__ RS, double *__restrict__ YY,
-               double *__restrict__ coef, P2P pp, int nblocks_reduce, const double *__restrict__ partial) {
-    if (ic[I_GATE] & kGateDone) return;
-    if (nblocks_reduce > 0) {
-        // single rank or peer-memory exchange: the fold of the block partials happens here (one launch less)
-        reduce_partials(m, nblocks_reduce, partial, pack, pp);
-        __threadfence();
-        __syncthreads();
-    }
-    if (pp.on) {
-        // wait for every rank's partial sums, then add them in rank order: every rank gets the same bits
-        __shared__ int bad;
-        if (threadIdx.x == 0) bad = 0;
-        __syncthreads();
-        if ((int)threadIdx.x < pp.nranks && !wait_epoch(pp.my_flags, threadIdx.x, pp.epoch)) bad = 1;
-        __syncthreads();
-        if (bad) {
-            if (threadIdx.x == 0) { ic[I_FLAGS] |= UPOL_FLAG_COMM; ic[I_GATE] |= kGateDone; }
-            return;
-        }
-        const int len = (m + 1) * kDotVals;
-        if ((int)threadIdx.x < len) {
-            double t = 0.0;
-            for (int r = 0; r < pp.nranks; ++r) t += ((volatile double *)pp.my_pack)[(int64_t)r * kMaxPack + threadIdx.x];
-            pack[threadIdx.x] = t;
-        }
-        __threadfence();
-        __syncthreads();
-    }
-    if (threadIdx.x) return;
+__device__ void control_body(int m, int mixed_enabled, int *__restrict__ ic, double *__restrict__ sc,
+                             double *__restrict__ pack, double *__restrict__ RS, double *__restrict__ YY,
+                             double *__restrict__ coef) {
+    const int maxiter = ic[I_MAXITER];
     const double *last = pack + m * kDotVals;
     const double p_y = last[0], yPy = last[1], p_g = last[2], yPg = last[3], gg = last[4], gPg = last[5];
     ic[I_NEVAL] += 1;
@@ -454,6 +436,164 @@ control_kernel(int m, int maxiter, int mixed_enabled, int *__restrict__ ic, doub
     ic[I_FIRST] = 0;
 }
 
+__global__ void __launch_bounds__(kMaxPack + 24)
+control_kernel(int m, int mixed_enabled, int *__restrict__ ic, double *__restrict__ sc,
+               double *__restrict__ pack, double *__restrict__ RS, double *__restrict__ YY,
+               double *__restrict__ coef, P2P pp, int nblocks_reduce, const double *__restrict__ partial) {
+    if (ic[I_GATE] & kGateDone) return;
+    if (nblocks_reduce > 0) {
+        // single rank or peer-memory exchange: the fold of the block partials happens here (one launch less)
+        reduce_partials(m, nblocks_reduce, partial, pack, pp);
+        __threadfence();
+        __syncthreads();
+    }
+    if (pp.on) {
+        // wait for every rank's partial sums, then add them in rank order: every rank gets the same bits
+        __shared__ int bad;
+        if (threadIdx.x == 0) bad = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < pp.nranks && !wait_epoch(pp.my_flags, threadIdx.x, pp.epoch)) bad = 1;
+        __syncthreads();
+        if (bad) {
+            if (threadIdx.x == 0) { ic[I_FLAGS] |= UPOL_FLAG_COMM; ic[I_GATE] |= kGateDone; }
+            return;
+        }
+        const int len = (m + 1) * kDotVals;
+        if ((int)threadIdx.x < len) {
+            double t = 0.0;
+            for (int r = 0; r < pp.nranks; ++r) t += ((volatile double *)pp.my_pack)[(int64_t)r * kMaxPack + threadIdx.x];
+            pack[threadIdx.x] = t;
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    if (threadIdx.x) return;
+    control_body(m, mixed_enabled, ic, sc, pack, RS, YY, coef);
+}
+
+// Single-rank slot, O(N) part in two launches instead of five.
+// (1) dots_fused_kernel: the y = m blocks apply the block preconditioner (Pg = P g, Py = P (g - g0)) to the elements
+//     they sum over, every block writes its partial inner products, and the block that finishes LAST folds the
+//     partials in fixed order and runs the controller (control_body) - no separate precondition / reduce / control
+//     launches.
+// (2) update_rows_kernel: one thread per Drude row moves its three components (new pair, new direction, new x) and
+//     writes the shell position / shell column / fp32 displacement record the next field pass reads - the job of
+//     prepare_shells_kernel, so that launch disappears from the loop too.
+__global__ void __launch_bounds__(kDotBlock)
+dots_fused_kernel(int m, int64_t n, int64_t e0, int64_t e1, int mixed_enabled, int *__restrict__ ic, double *__restrict__ sc,
+                  const double *__restrict__ S, const double *__restrict__ Y, const double *__restrict__ g,
+                  const double *__restrict__ g0, const double *__restrict__ p, double *__restrict__ Pg, double *__restrict__ Py,
+                  const int *__restrict__ row_mol, const int *__restrict__ mol_row0, const int *__restrict__ mol_nrow,
+                  const int64_t *__restrict__ blk_off, const double *__restrict__ blk,
+                  double *partial, double *__restrict__ pack, double *__restrict__ RS, double *__restrict__ YY,
+                  double *__restrict__ coef) {
+    if (ic[I_GATE] & kGateDone) return;
+    __shared__ double sm[kDotVals][kDotBlock / 32];
+    __shared__ int is_last;
+    const int l = blockIdx.y;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t e = e0 + (int64_t)blockIdx.x * kDotBlock + threadIdx.x; e < e1; e += (int64_t)gridDim.x * kDotBlock) {
+        const double ge = g[e], ye = ge - g0[e];
+        if (l < m) {
+            const double se = S[(int64_t)l * n + e], yl = Y[(int64_t)l * n + e];          // Y holds P y_l (P symmetric)
+            acc[0] += se * ye; acc[1] += yl * ye; acc[2] += se * ge; acc[3] += yl * ge;
+        } else {
+            const int mol = row_mol[e / 3];
+            const int64_t b0 = 3 * (int64_t)mol_row0[mol];
+            const int nb = 3 * mol_nrow[mol];
+            const double *row = blk + blk_off[mol] + (e - b0) * nb;
+            double pge = 0.0, pye = 0.0;
+            for (int j = 0; j < nb; ++j) {
+                const double gj = g[b0 + j];
+                pge += row[j] * gj;
+                pye += row[j] * (gj - g0[b0 + j]);
+            }
+            Pg[e] = pge; Py[e] = pye;
+            const double ae = p[e];
+            acc[0] += ae * ye; acc[1] += ye * pye; acc[2] += ae * ge; acc[3] += pye * ge;
+            acc[4] += ge * ge; acc[5] += ge * pge;
+        }
+    }
+    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        double v = acc[c];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (ln == 0) sm[c][w] = v;
+    }
+    __syncthreads();
+    const int len = (m + 1) * kDotVals;
+    if (threadIdx.x < 6) {
+        double t = 0.0;
+        for (int k = 0; k < kDotBlock / 32; ++k) t += sm[threadIdx.x][k];
+        partial[((int64_t)blockIdx.x * (m + 1) + l) * kDotVals + threadIdx.x] = t;
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ic + I_TICKET, 1) == (int)(gridDim.x * gridDim.y) - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if ((int)threadIdx.x < len) {
+        double t = 0.0;
+        if ((threadIdx.x % kDotVals) < 6)
+            for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(partial + (int64_t)b * len + threadIdx.x);
+        pack[threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x) return;
+    ic[I_TICKET] = 0;
+    control_body(m, mixed_enabled, ic, sc, pack, RS, YY, coef);
+}
+
+__global__ void __launch_bounds__(128)
+update_rows_kernel(int m, int64_t n, int row_lo, int row_hi, const int *__restrict__ ic, const double *__restrict__ sc,
+                   const double *__restrict__ coef, double *__restrict__ S, double *__restrict__ Y,
+                   double *__restrict__ x, double *__restrict__ x0, const double *__restrict__ g,
+                   double *__restrict__ g0, double *__restrict__ p, const double *__restrict__ Pg,
+                   const double *__restrict__ Py, const int *__restrict__ row_site, const double *__restrict__ r,
+                   const double *__restrict__ row_qs, double inv_grid, double *__restrict__ rowx, double *__restrict__ rowy,
+                   double *__restrict__ rowz, double4 *__restrict__ colsB, float4 *__restrict__ cols_d, float *__restrict__ cols_d2) {
+    if (ic[I_GATE] & kGateDone) return;
+    const int i = row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row_hi) return;
+    const bool accept = ic[I_ACCEPT] != 0, pushed = ic[I_PUSHED] != 0;
+    const int ns = ic[I_NEWSLOT];
+    const double alpha = sc[D_ALPHA], alpha_prev = sc[D_ALPHA_PREV], gamma = sc[D_GAMMA];
+    double xn[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int64_t e = 3 * (int64_t)i + c;
+        if (accept) {
+            const double ge = g[e];
+            if (pushed) {
+                S[(int64_t)ns * n + e] = alpha_prev * p[e];
+                Y[(int64_t)ns * n + e] = Py[e];                 // P y_new
+            }
+            double pn = -gamma * Pg[e];
+            for (int l = 0; l < m; ++l) {
+                const double a = coef[l], b = coef[kMaxHist + l];
+                if (a != 0.0 || b != 0.0) pn += -a * S[(int64_t)l * n + e] + gamma * b * Y[(int64_t)l * n + e];
+            }
+            const double xe = x[e];
+            x0[e] = xe; g0[e] = ge; p[e] = pn;
+            xn[c] = xe + alpha * pn;
+        } else {
+            xn[c] = x0[e] + alpha * p[e];
+        }
+        x[e] = xn[c];
+    }
+    // what prepare_shells_kernel would write for this row (system.cu)
+    const int st = row_site[i];
+    const double px = r[3 * st] - xn[0], py = r[3 * st + 1] - xn[1], pz = r[3 * st + 2] - xn[2];
+    rowx[i] = px; rowy[i] = py; rowz[i] = pz;
+    colsB[i] = make_double4(px, py, pz, row_qs[i]);
+    const float dx = (float)(xn[0] * inv_grid), dy = (float)(xn[1] * inv_grid), dz = (float)(xn[2] * inv_grid);
+    cols_d[i] = make_float4(-2.0f * dx, -2.0f * dy, -2.0f * dz, (float)row_qs[i]);
+    cols_d2[i] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
 // Element-wise update over the local slice: store the new pair, form the new direction, move x.
 __global__ void __launch_bounds__(256)
 update_kernel(int m, int64_t n, int64_t e0, int64_t e1, const int *__restrict__ ic, const double *__restrict__ sc,
@@ -585,7 +725,7 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
         build_blocks_kernel<<<(unsigned)((s->mol_hi - s->mol_lo + 63) / 64), 64, 0, st>>>(
             (int)s->mol_lo, (int)s->mol_hi, w->mol_row0, w->mol_nrow, w->blk_off, s->row_site, s->r, s->row_qs,
             s->row_k, s->th_ptr, s->th_row, s->th_u, w->blk);
-    init_state_kernel<<<1, 1, 0, st>>>(w->ic, w->sc, o->tol, mixed ? kGatePhaseMixed : kGatePhase64);
+    init_state_kernel<<<1, 1, 0, st>>>(w->ic, w->sc, o->tol, mixed ? kGatePhaseMixed : kGatePhase64, o->maxiter);
     UPOL_CUDA(cudaMemsetAsync(w->S, 0, sizeof(double) * (size_t)std::max(m, 1) * std::max<int64_t>(n, 1), st));
     UPOL_CUDA(cudaMemsetAsync(w->Y, 0, sizeof(double) * (size_t)std::max(m, 1) * std::max<int64_t>(n, 1), st));
     UPOL_CUDA(cudaMemsetAsync(w->p, 0, sizeof(double) * std::max<int64_t>(n, 1), st));
@@ -635,7 +775,7 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
             if (r) return r;
             ++s->launches;
         }
-        control_kernel<<<1, kMaxPack + 24, 0, st>>>(m, o->maxiter, mixed ? 1 : 0, w->ic, w->sc, w->pack, w->RS, w->YY, w->coef, pp,
+        control_kernel<<<1, kMaxPack + 24, 0, st>>>(m, mixed ? 1 : 0, w->ic, w->sc, w->pack, w->RS, w->YY, w->coef, pp,
                                                     nccl_between ? 0 : w->nblocks, w->partial);
         update_kernel<<<ublocks, 256, 0, st>>>(m, n, e0, e1, w->ic, w->sc, w->coef, w->S, w->Y, x, w->x0, w->g, w->g0, w->p, w->Pg, w->Py, pp);
         s->launches += 4;
@@ -673,6 +813,7 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
     EvalOpts ef;
     ef.precision = UPOL_FP64;
     ef.want_energy = true; ef.want_grad = false; ef.reduce_ranks = true;
+    if (pp.on) ef.gx = make_eval_xchg(s, false);      // the energy partials meet in the peers' mailboxes, no NCCL
     rc = sys_eval_compact(s, x, ef, w->e_final, w->g, st);
     if (rc) return rc;
     UPOL_CUDA(cudaMemcpyAsync(w->h_ic, w->ic, sizeof(int) * I_SIZE, cudaMemcpyDeviceToHost, st));

@@ -45,27 +45,32 @@ __device__ __forceinline__ void two_sum_acc(double &hi, double &lo, double x) {
     hi = s;
 }
 
-// q / r^3 from r^2 without forming 1/r (field-only variant): seed y, e = 1 - x y^2,
-// y^3 (1-e)^(-3/2) = y^3 (1 + 3e/2 + 15e^2/8 + O(e^3)); 7 DP ops, same O(e^3) ~ 1e-20 truncation.
+// q / r^3 from r^2 without forming 1/r (field-only variant): seed y (MUFU.RSQ64H, |e| <= 2^-22), e = 1 - x y^2,
+// y^3 (1-e)^(-3/2) = y^3 (1 + 3e/2 + O(e^2)); 6 DP ops.  The dropped 15 e^2 / 8 <= 1.1e-13 per term is far below
+// the 1e-10 bar of a gradient (the potential, whose row sums cancel to 1e-6 of their size, keeps the third-order
+// root below).
 __device__ __forceinline__ double q_over_r3_f64(double q, double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double y2 = y * y;
     const double e = fma(-x, y2, 1.0);
-    const double c = fma(fma(1.875, e, 1.5), e, 1.0);
+    const double c = fma(1.5, e, 1.0);
     return ((q * y) * y2) * c;
 }
 
 __device__ __forceinline__ double rsqrt_f64(double x) {
     // MUFU.RSQ64H seed (rel. error <= 2^-22) + one third-order (Halley) step:
-    // 1/sqrt(x) = y (1-e)^(-1/2),  e = 1 - x y^2  ->  y (1 + e/2 + 3e^2/8), error O(e^3) ~ 1e-20
+    // 1/sqrt(x) = y (1-e)^(-1/2),  e = 1 - x y^2  ->  y (1 + e (1/2 + 3e/8)), error O(e^3) ~ 1e-20.
+    // Written as y * fma(e, p, 1) rather than fma(y e, p, y): same five DP instructions, but none of them
+    // reads three distinct registers (a DFMA with three 64-bit register operands takes 3.1 cycles per warp
+    // instead of 2.2 - register-operand bandwidth, profiles/r02_ubench2.txt).
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double t = y * y;
-    double e = fma(-x, t, 1.0);
-    double p = fma(0.375, e, 0.5);
-    double q = y * e;
-    return fma(q, p, y);
+    const double t = y * y;
+    const double e = fma(-x, t, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double c = fma(e, p, 1.0);
+    return y * c;
 }
 
 // SPLITF (core-force pass): the fields of section A and section B are kept apart, because they are

@@ -179,7 +179,8 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
                      const int *__restrict__ th_ptr, const int *__restrict__ th_row,
                      const double *__restrict__ th_u, double *__restrict__ phi_static,
                      bool with_grad, double *__restrict__ gc, double *__restrict__ eblock,
-                     int *__restrict__ ticket, double *__restrict__ e_out, double *__restrict__ e_static, int e_flags) {
+                     int *__restrict__ ticket, double *__restrict__ e_out, double *__restrict__ e_static, int e_flags,
+                     const EvalXchg xg) {
     __shared__ double sm[kFinBlock / 32];
     __shared__ int is_last;
     __shared__ double fold[kFinLanes][kFinRows][kPartComps];
@@ -235,6 +236,15 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
         if (with_grad) {
             gc[3 * i] = gx; gc[3 * i + 1] = gy; gc[3 * i + 2] = gz;
             g2 = gx * gx + gy * gy + gz * gz;
+            if (xg.on && xg.push_grad) {
+                // fused all-gather: the row goes straight into every peer's gradient buffer (NVLink stores)
+                for (int rk = 0; rk < xg.nranks; ++rk) {
+                    if (rk == xg.rank) continue;
+                    double *pg = xg.peer_g[rk] + xg.g_off + 3 * (int64_t)i;
+                    pg[0] = gx; pg[1] = gy; pg[2] = gz;
+                }
+                __threadfence_system();
+            }
         }
     }
     const double s0 = block_sum<kFinBlock>(e_inter, sm);
@@ -245,7 +255,7 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
     if (threadIdx.x == 0) {
         double *o = eblock + kEblockComps * (int64_t)blockIdx.x;
         o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3; o[4] = s4;
-        __threadfence();
+        if (xg.on) __threadfence_system(); else __threadfence();
         is_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
@@ -262,7 +272,64 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
     }
     if (threadIdx.x == 0) {
         *ticket = 0;
-        write_energy_vector(e_out, res, e_static, e_flags);
+        if (!xg.on) {
+            write_energy_vector(e_out, res, e_static, e_flags);
+        } else {
+            // the rank's partial sums go into its slot of every rank's mailbox; then, after a system-wide fence
+            // (every block fenced its gradient stores before it took its ticket), the arrival epoch is raised
+            if (e_flags & kESaveStatic) e_static[0] = res[4];
+            if (e_flags & kEPutStatic) res[4] = e_static[0];
+            for (int rk = 0; rk < xg.nranks; ++rk) {
+                double *m = xg.peer_e[rk] + xg.e_off + xg.rank * UPOL_E_SIZE;
+                for (int c = 0; c < kEblockComps; ++c) m[c] = res[c];
+            }
+            __threadfence_system();
+            for (int rk = 0; rk < xg.nranks; ++rk) *((volatile int *)(xg.peer_flags[rk] + xg.rank)) = xg.epoch;
+        }
+    }
+}
+
+// A rank without rows still owes its peers an (all-zero) energy slot and its arrival epoch.
+__global__ void eval_xchg_empty_kernel(const EvalXchg xg) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (int rk = 0; rk < xg.nranks; ++rk) {
+        double *m = xg.peer_e[rk] + xg.e_off + xg.rank * UPOL_E_SIZE;
+        for (int c = 0; c < kEblockComps; ++c) m[c] = 0.0;
+    }
+    __threadfence_system();
+    for (int rk = 0; rk < xg.nranks; ++rk) *((volatile int *)(xg.peer_flags[rk] + xg.rank)) = xg.epoch;
+}
+
+// Spin until flags[i] >= epoch (raised by peer i through NVLink).  The time-out (~30 s) only guards against a
+// dead peer: ranks may enter a call seconds apart (host-side skew), which is not an error.
+__device__ __forceinline__ bool wait_epoch_long(const int *flags, int i, int epoch) {
+    const volatile int *f = flags + i;
+    const long long t0 = clock64();
+    while (*f < epoch) {
+        if (clock64() - t0 > 60000000000LL) return false;
+        __nanosleep(100);
+    }
+    __threadfence_system();
+    return true;
+}
+
+// Consumer side of the exchange: every peer's rows and energy partials have arrived once all epochs are in;
+// the energy vector is the sum of the mailbox slots in RANK ORDER (same bits on every rank).  A peer that never
+// delivers turns the energy into NaN instead of hanging the stream.
+__global__ void eval_xchg_wait_kernel(const EvalXchg xg, const int *__restrict__ my_flags, const double *__restrict__ my_e,
+                                      double *__restrict__ e_out) {
+    bool ok = true;
+    if ((int)threadIdx.x < xg.nranks) ok = wait_epoch_long(my_flags, threadIdx.x, xg.epoch);
+    ok = __all_sync(0xffffffffu, ok);
+    if (threadIdx.x) return;
+    double res[kEblockComps] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int rk = 0; rk < xg.nranks; ++rk)
+        for (int c = 0; c < kEblockComps; ++c) res[c] += ((const volatile double *)my_e)[xg.e_off + rk * UPOL_E_SIZE + c];
+    if (!ok) { for (int c = 0; c < kEblockComps; ++c) res[c] = nan(""); }
+    if (e_out != nullptr) {
+        e_out[UPOL_E_INTER] = res[0]; e_out[UPOL_E_INTRA] = res[1]; e_out[UPOL_E_SELF] = res[2]; e_out[UPOL_E_GNORM2] = res[3];
+        e_out[UPOL_E_STATIC] = res[4]; e_out[6] = 0.0; e_out[7] = 0.0;
+        e_out[UPOL_E_UIND] = (res[0] + res[1]) + res[2];
     }
 }
 
@@ -440,6 +507,8 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
     a.gate = o.gate;
     double *e = energy_dev ? energy_dev : s->energy;
     const bool reduce = o.reduce_ranks && s->nranks > 1;
+    EvalXchg xg = o.gx;
+    if (!reduce || !s->p2p) xg.on = 0;
     if (a.n_rows > 0) {
         const int split64 = choose_split(s, a.n_rows, a.n_tiles, fp64_rows_per_block());
         int split_pot = 0, split_f64 = 0, split_mx = 0;
@@ -497,15 +566,21 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
                                                        s->row_site, s->r, dcmp, s->row_qs, s->row_k,
                                                        s->th_ptr, s->th_row, s->th_u,
                                                        (o.want_energy && !diff_energy) ? s->phi_static : nullptr, o.want_grad, gcmp,
-                                                       s->eblock, s->ticket, e, s->e_static, e_flags);
+                                                       s->eblock, s->ticket, e, s->e_static, e_flags, xg);
         UPOL_CUDA(cudaGetLastError());
         s->launches += 2 + (s->nd > 0 ? 0 : -1);
         if (fuse_static) s->static_valid = true;
+    } else if (xg.on) {
+        eval_xchg_empty_kernel<<<1, 32, 0, st>>>(xg);
+        ++s->launches;
     } else {
         // a rank without rows contributes zeros (and its cached static sum, which is zero as well)
         UPOL_CUDA(cudaMemsetAsync(e, 0, UPOL_E_SIZE * sizeof(double), st));
     }
-    if (reduce) {
+    if (xg.on) {
+        eval_xchg_wait_kernel<<<1, 32, 0, st>>>(xg, s->xflags2, s->xe, e);
+        ++s->launches;
+    } else if (reduce) {
         int rc = comm_allreduce_sum(s, e, UPOL_E_SIZE, st);
         if (rc) return rc;
         assemble_energy_kernel<<<1, 32, 0, st>>>(e);
@@ -513,6 +588,18 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
     }
     UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
+}
+
+EvalXchg make_eval_xchg(upol_system *s, bool push_grad) {
+    EvalXchg x = {0, 0, 1, 0, 0, nullptr, nullptr, nullptr, 0, 0};
+    if (!s->p2p || s->nranks <= 1) return x;
+    x.on = 1; x.rank = s->rank; x.nranks = s->nranks;
+    x.epoch = ++s->epoch_eval;
+    x.push_grad = push_grad ? 1 : 0;
+    x.peer_g = s->d_peer_g; x.peer_e = s->d_peer_e; x.peer_flags = s->d_peer_flags2;
+    x.g_off = (int64_t)(x.epoch & 1) * 3 * s->nd;
+    x.e_off = (x.epoch & 1) * s->nranks * UPOL_E_SIZE;
+    return x;
 }
 
 int sys_gather_d(upol_system *s, const double *d_full, double *d_compact, cudaStream_t st) {
@@ -526,6 +613,27 @@ int sys_scatter_g(upol_system *s, const double *g_compact, double *g_full, cudaS
     // after the all-gather of a sharded run every row is present; a single rank shows its row range only
     const int64_t lo = s->nranks > 1 ? 0 : s->row_lo, hi = s->nranks > 1 ? s->nd : s->row_hi;
     scatter_grad_kernel<<<nblk(s->nsite, 256), 256, 0, st>>>((int)s->nsite, (int)lo, (int)hi, s->site_row, g_compact, g_full);
+    ++s->launches;
+    UPOL_CUDA(cudaGetLastError());
+    return UPOL_OK;
+}
+
+// Only the sites [site_lo, site_hi) of the (nsite,3) layout, from this rank's own rows (sharded host path).
+__global__ void scatter_grad_range_kernel(int site_lo, int site_hi, int row_lo, int row_hi, const int *__restrict__ site_row,
+                                          const double *__restrict__ compact, double *__restrict__ full) {
+    const int i = site_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= site_hi) return;
+    const int row = site_row[i];
+    const bool on = row >= row_lo && row < row_hi;
+    full[3 * i] = on ? compact[3 * row] : 0.0;
+    full[3 * i + 1] = on ? compact[3 * row + 1] : 0.0;
+    full[3 * i + 2] = on ? compact[3 * row + 2] : 0.0;
+}
+
+int sys_scatter_g_range(upol_system *s, const double *g_compact, double *g_full, int64_t site_lo, int64_t site_hi, cudaStream_t st) {
+    if (site_hi <= site_lo) return UPOL_OK;
+    scatter_grad_range_kernel<<<nblk(site_hi - site_lo, 256), 256, 0, st>>>((int)site_lo, (int)site_hi, (int)s->row_lo, (int)s->row_hi,
+                                                                            s->site_row, g_compact, g_full);
     ++s->launches;
     UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;

@@ -153,6 +153,25 @@ class UindSystem:
                 "upol_uind_energy_grad_host")
         return e, (g.reshape(self.nsite, 3) if want_grad else None)
 
+    def energy_grad_host_sharded(self, d, r_core=None, precision="fp64", energy=None, grad=None):
+        """Row-sharded host path (``upol_uind_energy_grad_host_sharded``): only this rank's site slice of
+        ``r_core`` (optional new geometry) and ``d`` goes up, only its slice of the gradient comes down.
+        ``energy`` (8,) / ``grad`` (N,3) may be preallocated (page-locked) numpy arrays; returns
+        (energy, grad, (site_lo, site_hi)) - grad holds this rank's rows only, the energy is the total."""
+        prec = {"fp64": L.FP64, "mixed": L.MIXED}[precision]
+        dd = d if isinstance(d, np.ndarray) and d.dtype == np.float64 and d.flags.c_contiguous else _np(d, np.float64)
+        rr = None
+        if r_core is not None:
+            rr = r_core if isinstance(r_core, np.ndarray) and r_core.dtype == np.float64 and r_core.flags.c_contiguous \
+                else _np(r_core, np.float64)
+        e = np.empty(L.E_SIZE, np.float64) if energy is None else energy
+        g = np.zeros(3 * self.nsite, np.float64) if grad is None else grad
+        lo, hi = C.c_int64(), C.c_int64()
+        L.check(L.lib().upol_uind_energy_grad_host_sharded(
+            self._h, rr.ctypes.data if rr is not None else None, dd.ctypes.data, prec, e.ctypes.data, g.ctypes.data,
+            C.byref(lo), C.byref(hi)), "upol_uind_energy_grad_host_sharded")
+        return e, g.reshape(self.nsite, 3), (lo.value, hi.value)
+
     def core_gradient(self, d):
         """dU_ind/dr_core at fixed displacements, (N,3) on device (force on the cores = minus this).
         Not in the reference (SURVEY 8f next #3)."""
