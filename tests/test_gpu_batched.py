@@ -57,6 +57,24 @@ def test_10k_perturbed_dimers():
         assert abs(info["U_ind"] - e[i, 0]) <= 1e-8 * abs(e[i, 0]) + 1e-14 * abs(e[i, 5])
 
 
+def test_10k_perturbed_dimers_sample_vs_newton_oracle():
+    """A sample of the 10 000 perturbed dimers against the CPU oracle's exact (Newton) minimum of the same geometry -
+    an external number for the batch, not the repo's own large-system engine."""
+    from oracle import uind_dense                 # checker only
+
+    z, k = _dimers()
+    r = synth.perturbed_dimers(z["r_core"], 10000, seed=5)
+    d, e, it = batched_minimize(r, z["q_core"], z["q_shell"], k, z["thole_u"], tol=1e-7)
+    e = e.cpu().numpy()
+    assert not e[:, 6].any()
+    rng = np.random.default_rng(3)
+    for i in [0, 311, 312, 9999] + list(rng.choice(10000, 8, replace=False)):
+        R, qis, qjs, qic, qjc, u, kk = uind_dense.dense_inputs(r[i], z["q_core"], z["q_shell"], k, z["thole_u"])
+        _, u_newton, gn = uind_dense.newton_minimum(R, np.zeros_like(r[i]), qis, qjs, qic, qjc, u, kk)
+        assert gn <= 1e-8
+        assert abs(e[i, 0] - u_newton) <= 1e-8 * abs(u_newton) + 1e-14 * abs(e[i, 5]), (i, e[i, 0], u_newton)
+
+
 def test_warm_start_and_water():
     s = synth.water_box(2, seed=3)
     r = np.stack([s.r_core, s.r_core + 0.01])

@@ -157,6 +157,7 @@ struct upol_system {
     double *cf_tmp = nullptr;        // [6*nd + 6*nsite] folded fields
     int64_t ns_pad = 0;
     bool static_valid = false;
+    int64_t geom_gen = 0;         // bumped by every geometry upload (captured graphs hold the box centre / grid by value)
 
     // row shard (Drude rows of molecules [mol_lo, mol_hi))
     int64_t mol_lo = 0, mol_hi = 0, row_lo = 0, row_hi = 0;
@@ -215,12 +216,14 @@ struct EvalOpts {
     const int *gate = nullptr;     // minimiser gate word (see kGate*)
     bool phase_switch = false;     // minimiser: launch both field kernels, gate picks one
     const double *d_full = nullptr; // displacements in the (nsite,3) layout: gathered into s->dc by the prepare kernel
+    bool shells_ready = false;      // shell rows / columns already match d (minimiser: written by its update kernel)
     EvalXchg gx = {0, 0, 1, 0, 0, nullptr, nullptr, nullptr, 0, 0};   // peer-memory exchange instead of NCCL (reduce_ranks)
 };
 EvalXchg make_eval_xchg(upol_system *s, bool push_grad);   // hands out the next evaluation epoch
 int sys_eval_compact(upol_system *s, const double *d_compact, const EvalOpts &o,
                      double *energy_dev, double *grad_compact, cudaStream_t st);
 int sys_static_part(upol_system *s, cudaStream_t st);
+int sys_prepare_shells(upol_system *s, const double *d_compact, cudaStream_t st);
 int sys_gather_d(upol_system *s, const double *d_full, double *d_compact, cudaStream_t st);
 int sys_scatter_g(upol_system *s, const double *g_compact, double *g_full, cudaStream_t st);
 int sys_scatter_g_range(upol_system *s, const double *g_compact, double *g_full, int64_t site_lo, int64_t site_hi, cudaStream_t st);

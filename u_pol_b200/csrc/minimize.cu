@@ -25,6 +25,7 @@
 // Polak-Ribiere-type preconditioned conjugate gradient under exact line searches.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -71,8 +72,9 @@ struct MinWs {
     cudaStream_t gstream = nullptr;          // capture needs a non-legacy stream
     cudaEvent_t gev[2] = {nullptr, nullptr};
     cudaGraphExec_t gexec = nullptr;
-    long long gkey[6] = {-1, -1, -1, -1, -1, -1};   // (m, mixed, check_every, row_lo, row_hi, geometry-independent launch shape)
+    long long gkey[6] = {-1, -1, -1, -1, -1, -1};   // (history | precision, chunk length, row range, x, geometry generation)
     bool graph_failed = false;
+    int64_t glaunches = 0;                   // kernels one replay of the graph launches
 };
 
 void ws_free(MinWs *w) {
@@ -707,7 +709,7 @@ static int ws_ensure(upol_system *s, int m, MinWs **out) {
     return UPOL_OK;
 }
 
-int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_min_result *res, cudaStream_t st) {
+int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_min_result *res, cudaStream_t st_caller) {
     memset(res, 0, sizeof(*res));
     int m = o->method == UPOL_CG ? 1 : (o->history > 0 ? o->history : 8);
     m = std::min(m, kMaxHist);
@@ -720,6 +722,23 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
     const int64_t e0 = 3 * s->row_lo, e1 = 3 * s->row_hi;
     const int64_t nloc = std::max<int64_t>(e1 - e0, 0);
     const unsigned ublocks = (unsigned)std::max<int64_t>(1, (nloc + 255) / 256);
+
+    // Single rank, open boundaries: the O(N) part of a slot is two fused launches (dots_fused_kernel,
+    // update_rows_kernel), the shells are kept current by the update, and chunks of slots are replayed from a CUDA
+    // graph (the whole solve under one jit in the reference, polarization.py:154,178-179).  Capture needs a
+    // non-legacy stream, so this path runs on the workspace's own stream, ordered after / before the caller's by events.
+    const bool fused = s->nranks == 1 && !s->ewald && s->nd > 0 && s->row_hi > s->row_lo;
+    static const bool no_graph = getenv("UPOL_NO_GRAPH") != nullptr;
+    cudaStream_t st = st_caller;
+    if (fused) {
+        if (!w->gstream) {
+            UPOL_CUDA(cudaStreamCreateWithFlags(&w->gstream, cudaStreamNonBlocking));
+            for (auto &e : w->gev) UPOL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        UPOL_CUDA(cudaEventRecord(w->gev[0], st_caller));
+        UPOL_CUDA(cudaStreamWaitEvent(w->gstream, w->gev[0], 0));
+        st = w->gstream;
+    }
 
     if (s->mol_hi > s->mol_lo)      // preconditioner blocks of this rank's molecules, current geometry
         build_blocks_kernel<<<(unsigned)((s->mol_hi - s->mol_lo + 63) / 64), 64, 0, st>>>(
@@ -740,6 +759,7 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
     eo.reduce_ranks = false;
     eo.gate = w->ic + I_GATE;
     eo.phase_switch = mixed;
+    eo.shells_ready = fused;          // update_rows_kernel keeps the shell rows / columns current
 
     P2P pp;
     memset(&pp, 0, sizeof(pp));
@@ -755,6 +775,10 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
         rc = comm_allreduce_sum(s, w->pack, 1, st);
         if (rc) return rc;
     }
+    if (fused) {                       // shells of the starting point; from here on the update kernel writes them
+        rc = sys_prepare_shells(s, x, st);
+        if (rc) return rc;
+    }
 
     auto enqueue_slot = [&]() -> int {
         if (pp.on) {
@@ -765,6 +789,17 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
         int r = sys_eval_compact(s, x, eo, s->energy, w->g, st);
         if (r) return r;
         dim3 dg((unsigned)w->nblocks, (unsigned)(m + 1));
+        if (fused) {
+            dots_fused_kernel<<<dg, kDotBlock, 0, st>>>(m, n, e0, e1, mixed ? 1 : 0, w->ic, w->sc, w->S, w->Y, w->g, w->g0, w->p,
+                                                        w->Pg, w->Py, w->row_mol, w->mol_row0, w->mol_nrow, w->blk_off, w->blk,
+                                                        w->partial, w->pack, w->RS, w->YY, w->coef);
+            update_rows_kernel<<<(unsigned)((s->row_hi - s->row_lo + 127) / 128), 128, 0, st>>>(
+                m, n, (int)s->row_lo, (int)s->row_hi, w->ic, w->sc, w->coef, w->S, w->Y, x, w->x0, w->g, w->g0, w->p, w->Pg, w->Py,
+                s->row_site, s->r, s->row_qs, s->inv_grid, s->rowx, s->rowy, s->rowz, s->cols + s->na_pad, s->cols_d, s->cols_d2);
+            s->launches += 2;
+            UPOL_CUDA(cudaGetLastError());
+            return UPOL_OK;
+        }
         precond_apply_kernel<<<ublocks, 256, 0, st>>>(e0, e1, w->ic, w->row_mol, w->mol_row0, w->mol_nrow, w->blk_off,
                                                       w->blk, w->g, w->g0, w->Pg, w->Py);
         dots_kernel<<<dg, kDotBlock, 0, st>>>(m, n, e0, e1, w->ic, w->S, w->Y, w->g, w->g0, w->p, w->Pg, w->Py, w->partial);
@@ -784,13 +819,53 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
         return UPOL_OK;
     };
 
+    // The graph of one chunk depends only on buffer addresses and launch shapes, never on values (tolerance, iteration
+    // limit and all line-search state live in device memory), so it is captured once per (history, precision, chunk
+    // length, row range, displacement vector) and replayed by every later minimisation of this system.
+    bool use_graph = fused && !no_graph && !w->graph_failed;
+    int64_t launches_per_chunk = 0;
+    if (use_graph) {
+        const long long key[6] = {m * 2 + (mixed ? 1 : 0), check_every, (long long)s->row_lo, (long long)s->row_hi, (long long)(intptr_t)x,
+                                  (long long)s->geom_gen};   // box centre and fixed-point grid are kernel arguments
+        if (!w->gexec || memcmp(key, w->gkey, sizeof(key)) != 0) {
+            if (w->gexec) { cudaGraphExecDestroy(w->gexec); w->gexec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            const int64_t l0 = s->launches;
+            bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                int r = UPOL_OK;
+                for (int c = 0; c < check_every && r == UPOL_OK; ++c) r = enqueue_slot();
+                ok = (cudaStreamEndCapture(st, &graph) == cudaSuccess) && r == UPOL_OK && graph != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&w->gexec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            w->glaunches = s->launches - l0;
+            s->launches = l0;
+            slots_in_call = 0;
+            if (!ok) {
+                cudaGetLastError();
+                w->graph_failed = true; use_graph = false;
+                if (w->gexec) { cudaGraphExecDestroy(w->gexec); w->gexec = nullptr; }
+            } else {
+                memcpy(w->gkey, key, sizeof(key));
+            }
+        }
+        launches_per_chunk = w->glaunches;
+    }
+
     // Enqueue chunks of slots, polling the done flag one chunk behind.
     const int max_slots = o->maxiter * 3 + kMaxLineSearch + 8;
     int enq = 0, buf = 0;
     bool done = false;
     bool pending[2] = {false, false};
     while (!done) {
-        for (int c = 0; c < check_every && enq < max_slots; ++c, ++enq) { rc = enqueue_slot(); if (rc) return rc; }
+        if (use_graph) {
+            UPOL_CUDA(cudaGraphLaunch(w->gexec, st));
+            enq += check_every;
+            s->launches += launches_per_chunk;
+        } else {
+            for (int c = 0; c < check_every && enq < max_slots; ++c, ++enq) { rc = enqueue_slot(); if (rc) return rc; }
+        }
         UPOL_CUDA(cudaMemcpyAsync(w->h_ic + buf * I_SIZE, w->ic, sizeof(int) * I_SIZE, cudaMemcpyDeviceToHost, st));
         UPOL_CUDA(cudaEventRecord(w->ev[buf], st));
         pending[buf] = true;
@@ -813,6 +888,7 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
     EvalOpts ef;
     ef.precision = UPOL_FP64;
     ef.want_energy = true; ef.want_grad = false; ef.reduce_ranks = true;
+    ef.shells_ready = fused;
     if (pp.on) ef.gx = make_eval_xchg(s, false);      // the energy partials meet in the peers' mailboxes, no NCCL
     rc = sys_eval_compact(s, x, ef, w->e_final, w->g, st);
     if (rc) return rc;
@@ -820,6 +896,10 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
     UPOL_CUDA(cudaMemcpyAsync(w->h_sc, w->e_final, sizeof(double) * UPOL_E_SIZE, cudaMemcpyDeviceToHost, st));
     UPOL_CUDA(cudaMemcpyAsync(w->h_sc + D_SIZE, w->sc, sizeof(double) * D_SIZE, cudaMemcpyDeviceToHost, st));
     UPOL_CUDA(cudaStreamSynchronize(st));
+    if (fused) {                       // later work on the caller's stream comes after everything enqueued here
+        UPOL_CUDA(cudaEventRecord(w->gev[1], st));
+        UPOL_CUDA(cudaStreamWaitEvent(st_caller, w->gev[1], 0));
+    }
     for (int i = 0; i < UPOL_E_SIZE; ++i) res->energy[i] = w->h_sc[i];
     res->gnorm = w->h_sc[D_SIZE + D_GNORM];
     res->energy[UPOL_E_GNORM2] = res->gnorm * res->gnorm;

@@ -476,6 +476,16 @@ int sys_static_part(upol_system *s, cudaStream_t st) {
     return UPOL_OK;
 }
 
+int sys_prepare_shells(upol_system *s, const double *d_compact, cudaStream_t st) {
+    if (s->nd <= 0) return UPOL_OK;
+    prepare_shells_kernel<<<nblk(s->nb_pad, 256), 256, 0, st>>>(
+        (int)s->nd, (int)s->nb_pad, s->row_site, s->r, nullptr, const_cast<double *>(d_compact), s->row_qs, s->inv_grid,
+        s->rowx, s->rowy, s->rowz, s->cols + s->na_pad, s->cols_d, s->cols_d2);
+    ++s->launches;
+    UPOL_CUDA(cudaGetLastError());
+    return UPOL_OK;
+}
+
 // One evaluation = prepare (shells, shell columns; also gathers d from the (nsite,3) layout when o.d_full is
 // set) -> pair kernel(s) -> finalize (fold, K qs, springs, Thole pairs, gradient rows; its last block sums
 // the energy vector).  Three launches, no memset.
@@ -496,10 +506,11 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
         int rc = sys_static_part(s, st);
         if (rc) return rc;
     }
-    if (s->nd > 0) {
+    if (s->nd > 0 && !o.shells_ready) {
         prepare_shells_kernel<<<nblk(s->nb_pad, 256), 256, 0, st>>>(
             (int)s->nd, (int)s->nb_pad, s->row_site, s->r, o.d_full, const_cast<double *>(dcmp), s->row_qs, s->inv_grid,
             s->rowx, s->rowy, s->rowz, s->cols + s->na_pad, s->cols_d, s->cols_d2);
+        ++s->launches;
     }
     PairArgs a = base_args(s);
     a.rx = s->rowx; a.ry = s->rowy; a.rz = s->rowz;
@@ -531,7 +542,7 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
             b.n_split = split64;
             b.dcomp = dcmp; b.col_qeff = s->col_qeff;
             b.gate_skip_mask = kGateDone | (o.phase_switch ? kGatePhaseMixed : 0);
-            const bool timed = s->timing && s->tev_used + 2 <= (int)s->tev.size();
+            const bool timed = s->timing && o.gate == nullptr && s->tev_used + 2 <= (int)s->tev.size();
             if (timed) cudaEventRecord(s->tev[s->tev_used], st);
             rc = launch_pair_fp64(b, o.want_energy, f64_field, fuse_static, st);
             if (timed) { cudaEventRecord(s->tev[s->tev_used + 1], st); s->tev_used += 2; }
@@ -548,7 +559,7 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
             b.exA_lo = s->exP_lo; b.exA_len = s->exP_len; b.exB_lo = s->exN_lo; b.exB_len = s->exN_len;
             b.n_split = choose_split(s, a.n_rows, b.n_tiles, diff_rows_per_block(diff_energy));
             b.gate_skip_mask = kGateDone | (o.phase_switch ? kGatePhase64 : 0);
-            const bool timed = s->timing && !f64_launch && s->tev_used + 2 <= (int)s->tev.size();
+            const bool timed = s->timing && o.gate == nullptr && !f64_launch && s->tev_used + 2 <= (int)s->tev.size();
             if (timed) cudaEventRecord(s->tev[s->tev_used], st);
             rc = launch_pair_diff(b, diff_energy, st);
             if (timed) { cudaEventRecord(s->tev[s->tev_used + 1], st); s->tev_used += 2; }
@@ -568,7 +579,7 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
                                                        (o.want_energy && !diff_energy) ? s->phi_static : nullptr, o.want_grad, gcmp,
                                                        s->eblock, s->ticket, e, s->e_static, e_flags, xg);
         UPOL_CUDA(cudaGetLastError());
-        s->launches += 2 + (s->nd > 0 ? 0 : -1);
+        ++s->launches;
         if (fuse_static) s->static_valid = true;
     } else if (xg.on) {
         eval_xchg_empty_kernel<<<1, 32, 0, st>>>(xg);
@@ -722,6 +733,7 @@ int sys_upload_positions(upol_system *s, const double *r_dev_or_null, cudaStream
     UPOL_CUDA(cudaGetLastError());
     s->launches += 2 + (s->nd > 0 ? 1 : 0);
     s->static_valid = false;
+    ++s->geom_gen;
     ewald_invalidate(s);
     return UPOL_OK;
 }
