@@ -221,7 +221,7 @@ static int upol_system_create_impl(upol_system **out, int device, int64_t nsite,
     TRY(dev_alloc(&s->part, part_elems));
     s->part_elems = part_elems;
     TRY(dev_alloc(&s->dc, 3 * s->nd)); TRY(dev_alloc(&s->gc, 3 * s->nd));
-    s->n_eblock = (int)((std::max<int64_t>(s->nd, nsite) + 31) / 32) + 1;   // finalize blocks hold 32 rows
+    s->n_eblock = (int)((std::max<int64_t>(s->nd, nsite) + 7) / 8) + 1;   // finalize blocks hold 32 rows (8 for small systems)
     TRY(dev_alloc(&s->eblock, 5 * (size_t)s->n_eblock));   // kEblockComps per finalize block
     TRY(dev_alloc(&s->ticket, 4));
     TRY(dev_alloc(&s->energy, UPOL_E_SIZE)); TRY(dev_alloc(&s->e_static, 2)); TRY(dev_alloc(&s->phi_static, s->nd_pad));

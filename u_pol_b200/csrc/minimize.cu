@@ -44,7 +44,7 @@ constexpr int kMaxLineSearch = 12;
 // integer control words
 enum { I_GATE = 0, I_ITER, I_NEVAL, I_HCOUNT, I_HHEAD, I_LS, I_FLAGS, I_ACCEPT, I_FIRST, I_NEWSLOT, I_PUSHED, I_MAXITER, I_TICKET, I_SIZE = 16 };
 // double control words
-enum { D_ALPHA = 0, D_ALPHA_PREV, D_PHI0, D_ALO, D_DLO, D_AHI, D_DHI, D_GAMMA, D_GNORM, D_GNORM0, D_TOL, D_SWITCH, D_SIZE = 16 };
+enum { D_ALPHA = 0, D_ALPHA_PREV, D_PHI0, D_ALO, D_DLO, D_AHI, D_DHI, D_GAMMA, D_GNORM, D_GNORM0, D_TOL, D_SWITCH, D_SWITCH_REL, D_SIZE = 16 };
 
 struct MinWs {
     int m = 0;
@@ -202,7 +202,7 @@ __global__ void wait_x_kernel(int *ic, P2P pp, int epoch_prev) {
     if (!__all_sync(0xffffffffu, ok) && threadIdx.x == 0) { ic[I_FLAGS] |= UPOL_FLAG_COMM; ic[I_GATE] |= kGateDone; }
 }
 
-__global__ void init_state_kernel(int *ic, double *sc, double tol, int phase_bits, int maxiter) {
+__global__ void init_state_kernel(int *ic, double *sc, double tol, int phase_bits, int maxiter, double switch_rel) {
     if (threadIdx.x || blockIdx.x) return;
     for (int i = 0; i < I_SIZE; ++i) ic[i] = 0;
     ic[I_MAXITER] = maxiter;
@@ -211,6 +211,7 @@ __global__ void init_state_kernel(int *ic, double *sc, double tol, int phase_bit
     ic[I_FIRST] = 1;
     sc[D_ALPHA] = 0.0;      // the first slot evaluates x itself
     sc[D_TOL] = tol;
+    sc[D_SWITCH_REL] = switch_rel;
     sc[D_GAMMA] = 1.0;
 }
 
@@ -316,7 +317,7 @@ __device__ void control_body(int m, int mixed_enabled, int *__restrict__ ic, dou
         sc[D_GNORM0] = gnorm;
         // mixed field error ~1.5e-6 of the gross field (= ||g(d=0)||).  Switching later (5e-5) was
         // measured to cost one extra iteration at 100 k Drudes, so the switch stays at 1e-3.
-        sc[D_SWITCH] = 1e-3 * gnorm;
+        sc[D_SWITCH] = sc[D_SWITCH_REL] * gnorm;
         accept = true;
     } else {
         const double phi0 = sc[D_PHI0];
@@ -744,7 +745,8 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
         build_blocks_kernel<<<(unsigned)((s->mol_hi - s->mol_lo + 63) / 64), 64, 0, st>>>(
             (int)s->mol_lo, (int)s->mol_hi, w->mol_row0, w->mol_nrow, w->blk_off, s->row_site, s->r, s->row_qs,
             s->row_k, s->th_ptr, s->th_row, s->th_u, w->blk);
-    init_state_kernel<<<1, 1, 0, st>>>(w->ic, w->sc, o->tol, mixed ? kGatePhaseMixed : kGatePhase64, o->maxiter);
+    static const double switch_rel = getenv("UPOL_MIXED_SWITCH") ? atof(getenv("UPOL_MIXED_SWITCH")) : 1e-3;
+    init_state_kernel<<<1, 1, 0, st>>>(w->ic, w->sc, o->tol, mixed ? kGatePhaseMixed : kGatePhase64, o->maxiter, switch_rel);
     UPOL_CUDA(cudaMemsetAsync(w->S, 0, sizeof(double) * (size_t)std::max(m, 1) * std::max<int64_t>(n, 1), st));
     UPOL_CUDA(cudaMemsetAsync(w->Y, 0, sizeof(double) * (size_t)std::max(m, 1) * std::max<int64_t>(n, 1), st));
     UPOL_CUDA(cudaMemsetAsync(w->p, 0, sizeof(double) * std::max<int64_t>(n, 1), st));

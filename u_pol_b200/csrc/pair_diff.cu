@@ -114,7 +114,7 @@ __device__ __forceinline__ void diff_site_careful(const int4 c, const float4 cd,
 // arithmetic is the packed one either way.
 template <int NP, bool POT, bool MASKED, int UNR>
 __device__ __forceinline__ void diff_tile_P(const int4 *__restrict__ shX, const float4 *__restrict__ shD, const float *__restrict__ shD2,
-                                            const int *sx, const int *sy, const int *sz, const int *lo, const int *len,
+                                            const float2 *__restrict__ shQ, const int *sx, const int *sy, const int *sz, const int *lo, const int *len,
                                             const f32x2 *T2x, const f32x2 *T2y, const f32x2 *T2z, const f32x2 *ND2,
                                             f32x2 *Fx, f32x2 *Fy, f32x2 *Fz, f32x2 *Hx, f32x2 *Hy, f32x2 *Hz, f32x2 *PA, f32x2 *PC) {
     const f32x2 mone2 = bcast2(-1.0f), m15 = bcast2(-1.5f);
@@ -156,18 +156,33 @@ __device__ __forceinline__ void diff_tile_P(const int4 *__restrict__ shX, const 
             }
             const f32x2 yA2 = mul2(yA, yA), yC2 = mul2(yC, yC);
             const f32x2 meA = fma2(A2, yA2, mone2), meC = fma2(C2, yC2, mone2);      // -(1 - |X|^2 y^2)
-            const f32x2 zA = mul2(pa, yA2), zC = mul2(pc, yC2);
-            // w_A + w_C with both seed corrections in one go; the -w_C d_j part is |d_j|/|A| times
-            // smaller than the gross terms and takes the uncorrected z_C
-            const f32x2 wS = fma2(fma2(zC, meC, mul2(zA, meA)), m15, add2(zA, zC));
-            Fx[p] = fma2(wS, Ax, Fx[p]); Fy[p] = fma2(wS, Ay, Fy[p]); Fz[p] = fma2(wS, Az, Fz[p]);
-            Hx[p] = fma2(zC, mx2, Hx[p]); Hy[p] = fma2(zC, my2, Hy[p]); Hz[p] = fma2(zC, mz2, Hz[p]);
+            if (POT) {
+                const f32x2 zA = mul2(pa, yA2), zC = mul2(pc, yC2);
+                // w_A + w_C with both seed corrections in one go; the -w_C d_j part is |d_j|/|A| times
+                // smaller than the gross terms and takes the uncorrected z_C
+                const f32x2 wS = fma2(fma2(zC, meC, mul2(zA, meA)), m15, add2(zA, zC));
+                Fx[p] = fma2(wS, Ax, Fx[p]); Fy[p] = fma2(wS, Ay, Fy[p]); Fz[p] = fma2(wS, Az, Fz[p]);
+                Hx[p] = fma2(zC, mx2, Hx[p]); Hy[p] = fma2(zC, my2, Hy[p]); Hz[p] = fma2(zC, mz2, Hz[p]);
+            } else {
+                // field only: w = y^3 q (1 + 1.5 e) with q and -1.5 q as broadcast column constants (one packed
+                // instruction less per site than the route over q y)
+                f32x2 q15A = bcast2(shQ[j].x), q15C = bcast2(shQ[j].y);
+                if (MASKED) {
+                    const bool e0 = (unsigned)(j - lo[2 * p]) < (unsigned)len[2 * p], e1 = (unsigned)(j - lo[2 * p + 1]) < (unsigned)len[2 * p + 1];
+                    q15A = pack2(e0 ? 0.f : shQ[j].x, e1 ? 0.f : shQ[j].x); q15C = pack2(e0 ? 0.f : shQ[j].y, e1 ? 0.f : shQ[j].y);
+                }
+                const f32x2 cA = fma2(meA, q15A, qc2), cC = fma2(meC, q15C, qs2);
+                const f32x2 wA = mul2(mul2(yA2, yA), cA), wC = mul2(mul2(yC2, yC), cC);
+                const f32x2 wS = add2(wA, wC);
+                Fx[p] = fma2(wS, Ax, Fx[p]); Fy[p] = fma2(wS, Ay, Fy[p]); Fz[p] = fma2(wS, Az, Fz[p]);
+                Hx[p] = fma2(wC, mx2, Hx[p]); Hy[p] = fma2(wC, my2, Hy[p]); Hz[p] = fma2(wC, mz2, Hz[p]);
+            }
         }
     }
 }
 
 template <int NP, bool POT, bool MASKED, int UNR>
-__device__ __forceinline__ void diff_tile_N(const int4 *__restrict__ shX, const int *sx, const int *sy, const int *sz,
+__device__ __forceinline__ void diff_tile_N(const int4 *__restrict__ shX, const float2 *__restrict__ shQ, const int *sx, const int *sy, const int *sz,
                                             const int *lo, const int *len, const f32x2 *T2x, const f32x2 *T2y,
                                             const f32x2 *T2z, const f32x2 *ND2, f32x2 *Fx, f32x2 *Fy, f32x2 *Fz, f32x2 *PA) {
     const f32x2 mone2 = bcast2(-1.0f), m15 = bcast2(-1.5f);
@@ -199,8 +214,18 @@ __device__ __forceinline__ void diff_tile_N(const int4 *__restrict__ shX, const 
             }
             const f32x2 yA2 = mul2(yA, yA);
             const f32x2 meA = fma2(A2, yA2, mone2);
-            const f32x2 zA = mul2(pa, yA2);
-            const f32x2 wA = fma2(mul2(zA, meA), m15, zA);
+            f32x2 wA;
+            if (POT) {
+                const f32x2 zA = mul2(pa, yA2);
+                wA = fma2(mul2(zA, meA), m15, zA);
+            } else {
+                f32x2 q15A = bcast2(shQ[j].x);
+                if (MASKED) {
+                    const bool e0 = (unsigned)(j - lo[2 * p]) < (unsigned)len[2 * p], e1 = (unsigned)(j - lo[2 * p + 1]) < (unsigned)len[2 * p + 1];
+                    q15A = pack2(e0 ? 0.f : shQ[j].x, e1 ? 0.f : shQ[j].x);
+                }
+                wA = mul2(mul2(yA2, yA), fma2(meA, q15A, qc2));
+            }
             Fx[p] = fma2(wA, Ax, Fx[p]); Fy[p] = fma2(wA, Ay, Fy[p]); Fz[p] = fma2(wA, Az, Fz[p]);
         }
     }
@@ -213,6 +238,7 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
     __shared__ int4 shX[kTileCols];
     __shared__ float4 shD[kTileCols];
     __shared__ float shD2[kTileCols];
+    __shared__ float2 shQ[POT ? 1 : kTileCols];     // field only: -1.5 q_core, -1.5 q_shell of the column
     if (a.gate != nullptr && (*a.gate & a.gate_skip_mask) != 0) return;
     const int4 *__restrict__ cols_x = static_cast<const int4 *>(a.cols);
     const float4 *__restrict__ cols_d = static_cast<const float4 *>(a.cols_d);
@@ -257,8 +283,11 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
         const bool isP = t < a.n_tiles_a;
         __syncthreads();
         for (int j = tid; j < kTileCols; j += kBlock) {
-            shX[j] = cols_x[base + j];
-            if (isP) { shD[j] = cols_d[base + j]; shD2[j] = cols_d2[base + j]; }
+            const int4 cx = cols_x[base + j];
+            shX[j] = cx;
+            float qsj = 0.f;
+            if (isP) { const float4 cd = cols_d[base + j]; shD[j] = cd; shD2[j] = cols_d2[base + j]; qsj = cd.w; }
+            if (!POT) shQ[POT ? 0 : j] = make_float2(-1.5f * __int_as_float(cx.w), -1.5f * qsj);
         }
         __syncthreads();
 
@@ -287,11 +316,11 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
             }
             const bool masked = __any_sync(0xffffffffu, need);
             if (isP) {
-                if (masked) diff_tile_P<NP, POT, true, UP>(shX, shD, shD2, sx, sy, sz, lo, len, T2x, T2y, T2z, ND2, Fx, Fy, Fz, Hx, Hy, Hz, PA, PC);
-                else diff_tile_P<NP, POT, false, UP>(shX, shD, shD2, sx, sy, sz, lo, len, T2x, T2y, T2z, ND2, Fx, Fy, Fz, Hx, Hy, Hz, PA, PC);
+                if (masked) diff_tile_P<NP, POT, true, UP>(shX, shD, shD2, shQ, sx, sy, sz, lo, len, T2x, T2y, T2z, ND2, Fx, Fy, Fz, Hx, Hy, Hz, PA, PC);
+                else diff_tile_P<NP, POT, false, UP>(shX, shD, shD2, shQ, sx, sy, sz, lo, len, T2x, T2y, T2z, ND2, Fx, Fy, Fz, Hx, Hy, Hz, PA, PC);
             } else {
-                if (masked) diff_tile_N<NP, POT, true, UN>(shX, sx, sy, sz, lo, len, T2x, T2y, T2z, ND2, Fx, Fy, Fz, PA);
-                else diff_tile_N<NP, POT, false, UN>(shX, sx, sy, sz, lo, len, T2x, T2y, T2z, ND2, Fx, Fy, Fz, PA);
+                if (masked) diff_tile_N<NP, POT, true, UN>(shX, shQ, sx, sy, sz, lo, len, T2x, T2y, T2z, ND2, Fx, Fy, Fz, PA);
+                else diff_tile_N<NP, POT, false, UN>(shX, shQ, sx, sy, sz, lo, len, T2x, T2y, T2z, ND2, Fx, Fy, Fz, PA);
             }
             const f32x2 half2 = bcast2(0.5f);
 #pragma unroll

@@ -297,7 +297,7 @@ template <int ROWS, int MINB>
 static void launch_fp64_variant(const PairArgs &a, bool with_pot, bool with_grad, bool fuse_static, cudaStream_t st) {
     dim3 grid((unsigned)((a.n_rows + kBlock * ROWS - 1) / (kBlock * ROWS)), (unsigned)a.n_split);
     if (with_pot && fuse_static) {
-        if (with_grad) pair_fp64_kernel<ROWS, true, true, 3, false, true><<<grid, kBlock, 0, st>>>(a);   // 3 resident blocks: <= 168 registers
+        if (with_grad) pair_fp64_kernel<ROWS, true, true, ROWS == 1 ? 4 : 3, false, true><<<grid, kBlock, 0, st>>>(a);   // 3 resident blocks: <= 168 registers
         else pair_fp64_kernel<ROWS, true, false, MINB, false, true><<<grid, kBlock, 0, st>>>(a);
     } else if (with_pot && with_grad)
         pair_fp64_kernel<ROWS, true, true, MINB><<<grid, kBlock, 0, st>>>(a);
@@ -314,7 +314,13 @@ int fp64_rows_per_block() { return kRowTile; }
 // busy), so the plain 2-rows / no-min-blocks build stays.
 int launch_pair_fp64(const PairArgs &a, bool with_pot, bool with_grad, bool fuse_static, cudaStream_t st) {
     if (a.n_rows <= 0) return UPOL_OK;
-    launch_fp64_variant<kRowsPerThread, 1>(a, with_pot, with_grad, fuse_static, st);
+    // Small systems (BASELINE config 2: 3 000 Drude rows): with 2 rows per thread the grid is only ~3 waves of
+    // resident blocks and the last, mostly empty wave costs 20 %; one row per thread doubles the block count.
+    static const int force_rows = getenv("UPOL_F64_ROWS") ? atoi(getenv("UPOL_F64_ROWS")) : 0;
+    const int64_t blocks2 = (int64_t)((a.n_rows + kRowTile - 1) / kRowTile) * a.n_split;
+    const bool rows1 = force_rows ? force_rows == 1 : (blocks2 < 148 * 3 * 6 && with_pot && fuse_static);   // measured: only the fused pass gains
+    if (rows1) launch_fp64_variant<1, 1>(a, with_pot, with_grad, fuse_static, st);
+    else launch_fp64_variant<kRowsPerThread, 1>(a, with_pot, with_grad, fuse_static, st);
     UPOL_CUDA(cudaGetLastError());
     return UPOL_OK;
 }

@@ -128,20 +128,22 @@ constexpr int kEblockComps = 5;   // per finalize block: inter, intra, self, |g|
 constexpr int kFinRows = 32;      // rows per finalize block: 32 rows x 4 split lanes
 constexpr int kFinLanes = kFinBlock / kFinRows;
 
-// Fold the column-split partials of one row.  A block handles kFinRows rows; thread (lx, ly) sums the
-// splits ly, ly+4, ... of row lx for components [c0, c0+NC) with independent loads in flight, and
-// the four lane sums are combined in fixed order by lane 0 (deterministic).  At small N the split
-// count reaches ~100 and a single thread per row would chain ~500 L2 loads.
-template <int NC>
+// Fold the column-split partials of one row.  A block handles FR rows; thread (lx, ly) sums the
+// splits ly, ly+FL, ... (FL = 128 / FR lanes) of row lx for components [c0, c0+NC) with independent loads in
+// flight, and the lane sums are combined in fixed order by lane 0 (deterministic).  At small N the split
+// count reaches ~100 and a single thread per row would chain ~500 L2 loads; small systems therefore use
+// FR = 8 (16 lanes per row, four times as many blocks), large ones FR = 32.
+template <int NC, int FR = kFinRows>
 __device__ __forceinline__ void fold_splits(const double *__restrict__ part, int64_t stride, int lr, bool live,
-                                            int n_split, int c0, double (*sm)[kFinRows][kPartComps], double *out) {
-    const int lx = threadIdx.x % kFinRows, ly = threadIdx.x / kFinRows;
+                                            int n_split, int c0, double (*sm)[FR][kPartComps], double *out) {
+    constexpr int FL = kFinBlock / FR;
+    const int lx = threadIdx.x % FR, ly = threadIdx.x / FR;
     double acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[c] = 0.0;
     if (live) {
 #pragma unroll 4
-        for (int s = ly; s < n_split; s += kFinLanes) {
+        for (int s = ly; s < n_split; s += FL) {
             const double *p = part + (int64_t)s * kPartComps * stride + (int64_t)c0 * stride + lr;
 #pragma unroll
             for (int c = 0; c < NC; ++c) acc[c] += p[(int64_t)c * stride];
@@ -153,7 +155,12 @@ __device__ __forceinline__ void fold_splits(const double *__restrict__ part, int
     __syncthreads();
     if (ly == 0) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) out[c] = ((sm[0][lx][c] + sm[1][lx][c]) + sm[2][lx][c]) + sm[3][lx][c];
+        for (int c = 0; c < NC; ++c) {
+            double t = sm[0][lx][c];
+#pragma unroll
+            for (int l = 1; l < FL; ++l) t += sm[l][lx][c];
+            out[c] = t;
+        }
     }
 }
 
@@ -170,6 +177,7 @@ __device__ __forceinline__ void write_energy_vector(double *__restrict__ e, cons
 
 // K4b + K2: per Drude row, fold the column-split partials, apply K*qs, add the spring and the
 // intra-molecular Thole pairs, write the gradient row, and emit per-block energy partials.
+template <int FR>
 __global__ void __launch_bounds__(kFinBlock)
 finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int n_split_mixed, int fused_static,
                      const int *__restrict__ gate, int phase_switch, const double *__restrict__ part, int64_t stride,
@@ -183,20 +191,20 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
                      const EvalXchg xg) {
     __shared__ double sm[kFinBlock / 32];
     __shared__ int is_last;
-    __shared__ double fold[kFinLanes][kFinRows][kPartComps];
+    __shared__ double fold[kFinBlock / FR][FR][kPartComps];
     const int gw = gate ? *gate : 0;
     if (gw & kGateDone) return;
     // which field kernel ran decides how many column splits hold force partials
     const int n_split_f = (phase_switch && (gw & kGatePhaseMixed)) ? n_split_mixed : n_split_f64;
-    const int lr = blockIdx.x * kFinRows + threadIdx.x % kFinRows;
+    const int lr = blockIdx.x * FR + threadIdx.x % FR;
     const bool live = lr < n_rows;
-    const bool owner = live && threadIdx.x < kFinRows;
+    const bool owner = live && threadIdx.x < FR;
     double pot[2] = {0.0, 0.0}, frc[3] = {0.0, 0.0, 0.0}, stat[1] = {0.0};
-    if (n_split_pot > 0) fold_splits<2>(part, stride, lr, live, n_split_pot, 0, fold, pot);
-    if (with_grad) fold_splits<3>(part, stride, lr, live, n_split_f, 2, fold, frc);
+    if (n_split_pot > 0) fold_splits<2, FR>(part, stride, lr, live, n_split_pot, 0, fold, pot);
+    if (with_grad) fold_splits<3, FR>(part, stride, lr, live, n_split_f, 2, fold, frc);
     // fused pass: the static potential of the row arrives as slot 5 of the same launch; it is kept
     // (phi_static) so that later evaluations of this geometry need not form it again
-    if (fused_static) fold_splits<1>(part, stride, lr, live, n_split_pot, 5, fold, stat);
+    if (fused_static) fold_splits<1, FR>(part, stride, lr, live, n_split_pot, 5, fold, stat);
     double e_inter = 0.0, e_intra = 0.0, e_self = 0.0, g2 = 0.0, e_stat = 0.0;
     if (owner) {
         const int i = row0 + lr;
@@ -569,15 +577,18 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
             if (!o.phase_switch) split_f64 = b.n_split;   // no gate: the mixed partials are THE field
             if (diff_energy) split_pot = b.n_split;
         }
-        const int nb = (int)nblk(a.n_rows, kFinRows);
+        // small systems: 8 rows per finalize block (16 lanes fold the ~100 column splits of a row), else 32
+        const bool fin8 = a.n_rows <= 16384 && std::max(split_pot, std::max(split_f64, split_mx)) >= 16;
+        const int nb = (int)nblk(a.n_rows, fin8 ? 8 : kFinRows);
         const int e_flags = ((o.want_energy && !diff_energy && !fuse_static) ? kEPutStatic : 0) | (reduce ? 0 : kETotal) |
                             (fuse_static ? kESaveStatic : 0);
-        finalize_rows_kernel<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, split_pot, split_f64, split_mx, fuse_static ? 1 : 0,
-                                                       o.gate, o.phase_switch ? 1 : 0, s->part, a.part_stride,
-                                                       s->row_site, s->r, dcmp, s->row_qs, s->row_k,
-                                                       s->th_ptr, s->th_row, s->th_u,
-                                                       (o.want_energy && !diff_energy) ? s->phi_static : nullptr, o.want_grad, gcmp,
-                                                       s->eblock, s->ticket, e, s->e_static, e_flags, xg);
+        auto fin = fin8 ? finalize_rows_kernel<8> : finalize_rows_kernel<kFinRows>;
+        fin<<<nb, kFinBlock, 0, st>>>(a.n_rows, a.row0, split_pot, split_f64, split_mx, fuse_static ? 1 : 0,
+                                      o.gate, o.phase_switch ? 1 : 0, s->part, a.part_stride,
+                                      s->row_site, s->r, dcmp, s->row_qs, s->row_k,
+                                      s->th_ptr, s->th_row, s->th_u,
+                                      (o.want_energy && !diff_energy) ? s->phi_static : nullptr, o.want_grad, gcmp,
+                                      s->eblock, s->ticket, e, s->e_static, e_flags, xg);
         UPOL_CUDA(cudaGetLastError());
         ++s->launches;
         if (fuse_static) s->static_valid = true;
