@@ -383,14 +383,16 @@ __global__ void __launch_bounds__(kBlock, MINB) pair_diff_kernel(const PairArgs 
     }
 }
 
-// Launch shapes measured on the 100 k-Drude box (profiles/r02_diff_variants.txt): with the energy,
-// 2 rows per thread and 4 resident blocks (128 registers) 22.8 ms against 24.8 ms for 4 rows (246
-// registers, 2 blocks); field only, 4 rows (164 registers, 3 blocks) 14.3 ms against 14.7 ms.  Issuing the
-// FMAs that have three distinct register-pair operands as two scalar FFMAs each was measured slower
-// (25.0 ms / 15.0 ms) although such an FFMA2 costs 4.0 cycles and two FFMAs 3.2 in isolation
-// (scripts/ubench.cu, profiles/r02_ubench.txt): the loop is bound by register-file operand reads, and
-// the scalar form adds issue slots without removing any.
-
+// Launch shapes measured on the 100 k-Drude box (profiles/r02_diff_variants.txt, r02_variants_switch.txt): with
+// the energy, 2 rows per thread and 4 resident blocks (124-128 registers) 23.0 ms against 24.8 ms for 4 rows (246
+// registers, 2 blocks); field only, every shape between 2 rows / 6 blocks (80 registers) and 4 rows / 2 blocks
+// (172 registers) lands within 13.8-14.5 ms - occupancy is not the limiter.  ncu (profiles/r02_ncu_full_pairs.txt):
+// FMA pipe 65 % busy, XU (MUFU) 44 % / 69 % with the energy, ALU (IADD3, I2FP) 36 %, issue slots 62 %, top
+// stalls math-pipe throttle, fixed-latency wait and dispatch stall.  What the loop saturates is the register
+// file's read bandwidth (~2 operand words per lane and cycle, scripts/ubench2.cu: an FFMA2 with three 64-bit
+// register operands takes 3.1 cycles, with two 2.1): ~114 operand words per (row pair, polarisable site)
+// over all pipes, i.e. ~57 cycles at best, against ~68 measured.  Issuing FFMA2s with three register pairs as two
+// scalar FFMAs each was measured slower (25.0 ms / 15.0 ms): it adds issue slots without removing operand reads.
 
 // UPOL_DIFF_VARIANT (sweeps only): other launch shapes / unroll factors of the same kernel
 static int diff_variant() {
@@ -402,7 +404,7 @@ static int diff_variant() {
 int diff_rows_per_block(bool with_pot) {
     const int v = diff_variant();
     if (with_pot) return kBlock * (v == 5 ? 4 : 2);
-    return kBlock * (v == 2 ? 2 : 4);
+    return kBlock * ((v == 0 || v == 3) ? 2 : 4);
 }
 
 template <int ROWS, bool POT, int MINB, int UP, int UN>
@@ -418,18 +420,18 @@ int launch_pair_diff(const PairArgs &a, bool with_pot, cudaStream_t st) {
         switch (v) {
             case 1: launch_diff<2, true, 3, 2, 4>(a, st); break;
             case 2: launch_diff<2, true, 4, 1, 2>(a, st); break;
-            case 3: launch_diff<2, true, 4, 4, 4>(a, st); break;
+            case 3: launch_diff<2, true, 4, 2, 4>(a, st); break;
             case 4: launch_diff<2, true, 5, 2, 4>(a, st); break;
             case 5: launch_diff<4, true, 3, 1, 2>(a, st); break;
-            default: launch_diff<2, true, 4, 2, 4>(a, st); break;
+            default: launch_diff<2, true, 4, 4, 4>(a, st); break;
         }
     } else {
         switch (v) {
-            case 1: launch_diff<4, false, 3, 1, 2>(a, st); break;
-            case 2: launch_diff<2, false, 4, 2, 4>(a, st); break;
-            case 3: launch_diff<4, false, 1, 1, 2>(a, st); break;
-            case 4: launch_diff<4, false, 2, 2, 4>(a, st); break;
-            default: launch_diff<4, false, 1, 2, 4>(a, st); break;
+            case 1: launch_diff<4, false, 1, 2, 4>(a, st); break;
+            case 2: launch_diff<4, false, 3, 2, 4>(a, st); break;
+            case 3: launch_diff<2, false, 6, 2, 4>(a, st); break;
+            case 4: launch_diff<4, false, 3, 1, 2>(a, st); break;
+            default: launch_diff<2, false, 4, 2, 4>(a, st); break;
         }
     }
     UPOL_CUDA(cudaGetLastError());
