@@ -262,6 +262,22 @@ def run_reference_batched(args):
     print(json.dumps(out), flush=True)
 
 
+class _StdoutToStderr:
+    """NCCL announces its version on stdout when a communicator is created; rank 0's stdout must carry exactly one
+    JSON line, so file descriptor 1 points at stderr while communicators are being set up."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 class Dist:
     """torch.distributed plumbing shared by the configs."""
 
@@ -279,7 +295,9 @@ class Dist:
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            dist.init_process_group("nccl", device_id=self.dev)
+            with _StdoutToStderr():
+                dist.init_process_group("nccl", device_id=self.dev)
+                dist.barrier()                       # creates the communicator (and prints NCCL's banner) now
         self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=self.dev)   # > 126 MB L2
 
     def barrier(self):
@@ -396,7 +414,8 @@ def run_energy_grad(args):
     sysm = UindSystem.from_drude_system(s, device=D.local_rank)
     exchange = "none"
     if D.world > 1:
-        sysm.attach_process_group()
+        with _StdoutToStderr():
+            sysm.attach_process_group()
         exchange = ("peer-memory stores (CUDA IPC/NVLink) fused into the finalize / update kernels"
                     if getattr(sysm, "p2p", False) else "nccl")
     d_dev = torch.as_tensor(d_host.reshape(-1)).to(D.dev)
@@ -512,26 +531,34 @@ def run_energy_grad(args):
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "pair_fp64_kernel<POT,GRAD,FUSE> (main pass + fused static potential)",
                          "achieved": achieved, "peak": peak64 / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak64 / 1e12),
-                         "peak_source": "measured on this box: upol_measure_fma_peak (DFMA chain = what the FP64 pipe sustains: "
-                                        "91.6 % of the rate ncu calls 100 %, profiles/r02_ubench_ncu_summary.txt); "
+                         "peak_source": "measured on this box: upol_measure_fma_peak (register-resident DFMA chains; the FP64 pipe "
+                                        "sustains one warp instruction per 2.22 cycles per sub-partition at any ILP / occupancy, "
+                                        "profiles/r02_ubench2.txt, i.e. 90 % of the 2-cycle rate ncu calls 100 %); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "kernel_ms": k64_ms, "launches_timed": k64_n,
                          "flops_per_launch": flops_full_local,
                          "interactions_per_launch": inter_local, "static_interactions_per_launch": inter_static_local,
                          "flop_per_interaction": FLOP_PER_INTERACTION, "flop_per_static_interaction": FLOP_PER_STATIC_INTERACTION,
                          "fp64_pipe_active_pct_ncu": ncu.get("pair_fp64_kernel_fp64_pipe_active_pct"),
-                         "traffic": ncu.get("pair_fp64_kernel_dram_bytes_per_launch"),
+                         "traffic": ncu.get("pair_fp64_kernel_dram_bytes_per_launch") if D.world == 1 else None,
+                         "traffic_read": ncu.get("pair_fp64_kernel_dram_read_bytes") if D.world == 1 else None,
+                         "traffic_write": ncu.get("pair_fp64_kernel_dram_write_bytes") if D.world == 1 else None,
+                         "algorithmic_bytes": 80 * n + 24 * nd,
                          "traffic_source": ncu.get("source")},
             "mixed_step": {"ms_per_step": mx_ms, "value": pairs_per_step / (mx_ms * 1e-3), "unit": UNIT,
                            "e2e_ms_per_step": mx_e2e_ms, "kernel": "pair_diff_kernel<POT> (energy + field, difference form)",
                            "kernel_ms": kmx_ms, "achieved": flops_full_local / (kmx_ms * 1e-3) / 1e12, "peak": peak32 / 1e12,
                            "unit_roofline": "TFLOP/s", "frac": flops_full_local / (kmx_ms * 1e-3) / peak32,
-                           "bound": "fp32 register-operand bandwidth (2 x 32-bit reads per lane and cycle; FMAs with three "
-                                    "live operands cannot exceed 2/3 of the FFMA-chain peak, profiles/r02_ubench.txt)",
+                           "bound": "register-file read bandwidth (~2 operand words per lane and cycle over all pipes: an FFMA2 "
+                                    "with three 64-bit register operands takes 3.1 cycles, with two 2.1, profiles/r02_ubench2.txt) "
+                                    "and, with the energy, the XU pipe (5 MUFU per row and polarisable site, 69 % busy)",
                            "fma_pipe_active_pct_ncu": ncu.get("pair_diff_kernel_fma_pipe_active_pct"),
                            "xu_pipe_active_pct_ncu": ncu.get("pair_diff_kernel_xu_pipe_active_pct"),
                            "traffic": ncu.get("pair_diff_kernel_dram_bytes_per_launch"),
                            "field_only_kernel_ms": kfield_ms,
+                           "field_only_traffic": ncu.get("pair_diff_field_kernel_dram_bytes_per_launch"),
+                           "field_only_fma_pipe_active_pct_ncu": ncu.get("pair_diff_field_kernel_fma_pipe_active_pct"),
+                           "field_only_xu_pipe_active_pct_ncu": ncu.get("pair_diff_field_kernel_xu_pipe_active_pct"),
                            "field_only_achieved": FLOP_PER_INTERACTION * inter_local / (kfield_ms * 1e-3) / 1e12,
                            "field_only_frac": FLOP_PER_INTERACTION * inter_local / (kfield_ms * 1e-3) / peak32,
                            "error_vs_fp64": mixed_err, "U_ind": float(em[0]), "U_ind_e2e": float(emx_out[0])},
@@ -562,7 +589,8 @@ def run_minimise(args):
     nd = int((s.q_shell != 0).sum())
     sysm = UindSystem.from_drude_system(s, device=D.local_rank)
     if D.world > 1:
-        sysm.attach_process_group()
+        with _StdoutToStderr():
+            sysm.attach_process_group()
     infos = []
 
     def step():
@@ -574,6 +602,12 @@ def run_minimise(args):
     launches = (sysm.launch_count() - l0) * args.steps // (args.steps + warmup)
     info = infos[-1]
     assert info["flags"] == 0 and info["gnorm"] <= 1e-4, info
+    # the other arithmetic mode on the same line (fp32 field far from the minimum, fp64 for the last iterations)
+    other = "mixed" if args.precision == "fp64" else "fp64"
+    other_infos = []
+    ms_o, _, _ = D.timed_steps(lambda: other_infos.append(sysm.minimize(tol=1e-4, precision=other)[1]), args.steps, warmup)
+    io = other_infos[-1]
+    assert io["flags"] == 0 and io["gnorm"] <= 1e-4 and abs(io["U_ind"] - info["U_ind"]) <= 1e-9 * abs(info["U_ind"]), (io, info)
     # end to end through the C ABI with host buffers: positions up, zeros up, minimiser down
     r_host = np.ascontiguousarray(s.r_core.reshape(-1))
     d_host = np.zeros(3 * n)
@@ -613,6 +647,8 @@ def run_minimise(args):
                           "l2": "flushed between timed steps (256 MiB write, untimed)", "parallelism": f"row-shard x{D.world}"},
                "iterations": info["iterations"], "evaluations": info["evaluations"], "U_ind": info["U_ind"], "gnorm": info["gnorm"],
                "ms_per_evaluation_slot": ms / info["evaluations"],
+               other: {"value": ms_o * 1e-3, "unit": "s", "iterations": io["iterations"], "evaluations": io["evaluations"],
+                       "U_ind": io["U_ind"], "gnorm": io["gnorm"]},
                "e2e": {"value": e2e_ms * 1e-3, "unit": "s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(r_host.nbytes + d_host.nbytes),
                        "d2h_bytes_per_step": int(d_host.nbytes)},
                "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall}
