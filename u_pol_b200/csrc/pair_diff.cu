@@ -38,7 +38,7 @@
 // its tile-local sums are discarded when they come out non-finite or absurdly large.
 //
 // FMA-pipe instructions per (row, polarisable site): 45 with the energy, 26 field only; per (row,
-// other site) 23 / 12; MUFU 5 / 2 and 3 / 1.
+// other site) 23 / 12; MUFU 4 / 2 and 3 / 1.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -149,8 +149,11 @@ __device__ __forceinline__ void diff_tile_P(const int4 *__restrict__ shX, const 
                 const f32x2 DC = add2(DA, DCA);                                         // |C|^2 - |R|^2
                 const f32x2 yR = rsqrt2(R2);
                 const f32x2 nR = mul2(R2, yR);
-                const f32x2 uA = mul2(yR, rcp2(fma2(A2, yA, nR)));
-                const f32x2 uC = mul2(yR, rcp2(fma2(C2, yC, nR)));
+                // 1/(|A|+|R|) and 1/(|C|+|R|) from ONE reciprocal of their product: the XU pipe (MUFU) is the
+                // busiest pipe of this kernel (69 %, stalls on the MIO queue), two packed multiplies are cheaper
+                const f32x2 sA = fma2(A2, yA, nR), sC = fma2(C2, yC, nR);
+                const f32x2 yRt = mul2(yR, rcp2(mul2(sA, sC)));
+                const f32x2 uA = mul2(yRt, sC), uC = mul2(yRt, sA);
                 PA[p] = fma2(pa, mul2(DA, uA), PA[p]);        // -qc [f(A) - f(R)]
                 PC[p] = fma2(pc, mul2(DC, uC), PC[p]);        // -qs [f(C) - f(R)]
             }
@@ -418,12 +421,12 @@ int launch_pair_diff(const PairArgs &a, bool with_pot, cudaStream_t st) {
     const int v = diff_variant();
     if (with_pot) {
         switch (v) {
-            case 1: launch_diff<2, true, 3, 2, 4>(a, st); break;
+            case 1: launch_diff<2, true, 4, 4, 4>(a, st); break;
             case 2: launch_diff<2, true, 4, 1, 2>(a, st); break;
             case 3: launch_diff<2, true, 4, 2, 4>(a, st); break;
             case 4: launch_diff<2, true, 5, 2, 4>(a, st); break;
             case 5: launch_diff<4, true, 3, 1, 2>(a, st); break;
-            default: launch_diff<2, true, 4, 4, 4>(a, st); break;
+            default: launch_diff<2, true, 3, 2, 4>(a, st); break;
         }
     } else {
         switch (v) {
