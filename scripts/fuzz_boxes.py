@@ -11,7 +11,7 @@ from u_pol_b200.engine import UindSystem
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 rng = np.random.default_rng(2024)
 bad = 0
-worst = dict(dE=0.0, dg=0.0, dmix=0.0, dmin=0.0, it=0)
+worst = dict(dE=0.0, dg=0.0, dmix=0.0, dmin=0.0, it=0, dEm=0.0)
 for case in range(n_cases):
     maker = synth.water_box if case % 2 == 0 else synth.imidazole_box
     nmol = int(rng.integers(30, 900))
@@ -23,6 +23,9 @@ for case in range(n_cases):
     e, g = sys_.energy_grad(D)
     g = g.cpu().numpy().reshape(g_ref.shape)
     gm = sys_.energy_grad(D, precision="mixed", want_energy=False)[1].cpu().numpy().reshape(g_ref.shape)
+    em, gme = sys_.energy_grad(D, precision="mixed")             # energy AND gradient from the fp32 difference-form pass
+    dEm = abs(float(em[0]) - e_ref[0]) / abs(e_ref[0])
+    dgme = np.abs(gme.cpu().numpy().reshape(g_ref.shape) - g_ref).max() / np.abs(g_ref).max()
     dE = abs(float(e[0]) - e_ref[0]) / abs(e_ref[0])
     dg = np.abs(g - g_ref).max() / np.abs(g_ref).max()
     dmix = np.abs(gm - g_ref).max() / np.abs(g_ref).max()
@@ -35,9 +38,10 @@ for case in range(n_cases):
     its = [res[k]["iterations"] for k in res]
     worst["dE"] = max(worst["dE"], dE); worst["dg"] = max(worst["dg"], dg); worst["dmix"] = max(worst["dmix"], dmix)
     worst["dmin"] = max(worst["dmin"], dmin); worst["it"] = max(worst["it"], max(its[:2]))
-    if dE > 5e-10 or dg > 1e-10 or dmix > 1e-5 or dmin > 1e-8 or any(flags):
+    worst["dEm"] = max(worst["dEm"], dEm); worst["dmix"] = max(worst["dmix"], dgme)
+    if dE > 5e-10 or dg > 1e-10 or dmix > 1e-5 or dmin > 1e-8 or any(flags) or dEm > 1e-5 or dgme > 1e-5:
         bad += 1
-        print(f"case {case} {maker.__name__} nmol {nmol} seed {seed}: dE {dE:.1e} dg {dg:.1e} dmix {dmix:.1e} dmin {dmin:.1e} flags {flags} its {its}", flush=True)
+        print(f"case {case} {maker.__name__} nmol {nmol} seed {seed}: dE {dE:.1e} dg {dg:.1e} dmix {dmix:.1e} dEmixed {dEm:.1e} dmin {dmin:.1e} flags {flags} its {its}", flush=True)
     sys_.close()
-print(f"{n_cases} boxes: {bad} failing; worst dE {worst['dE']:.2e} dg {worst['dg']:.2e} dmixed {worst['dmix']:.2e} dmin {worst['dmin']:.2e} max L-BFGS iterations {worst['it']}")
+print(f"{n_cases} boxes: {bad} failing; worst dE {worst['dE']:.2e} dg {worst['dg']:.2e} dmixed {worst['dmix']:.2e} dE_mixed {worst['dEm']:.2e} dmin {worst['dmin']:.2e} max L-BFGS iterations {worst['it']}")
 sys.exit(min(bad, 100))
