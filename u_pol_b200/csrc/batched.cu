@@ -14,6 +14,8 @@
 #include <new>
 #include <vector>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "thole.cuh"
 
@@ -298,6 +300,20 @@ __global__ void batched_bfgs_kernel(BatchTopo t, const double *__restrict__ site
 
 using namespace upol;
 
+namespace {
+struct TopoEntry {
+    int device = -1;
+    std::vector<double> hd;
+    std::vector<int> hi;
+    double *dblob = nullptr;
+    int *iblob = nullptr;
+    uint64_t stamp = 0;
+};
+std::mutex g_topo_mutex;
+std::vector<TopoEntry> g_topo_cache;
+uint64_t g_topo_stamp = 0;
+}  // namespace
+
 static int batched_minimize_impl(int device, int64_t nbatch, int64_t nsite, const double *r_core_dev,
                                          double *d_dev, const double *q_core, const double *q_shell,
                                          const double *k, const int32_t *mol_id, int64_t npair,
@@ -308,16 +324,10 @@ static int batched_minimize_impl(int device, int64_t nbatch, int64_t nsite, cons
         !energy_dev || npair < 0)
         return UPOL_ERR_ARG;
     if (nbatch == 0) return UPOL_OK;
-    // scratch + device switch undone on EVERY exit path (early CUDA errors included)
+    // device switch undone on EVERY exit path (early CUDA errors included)
     struct Scope {
         int prev = -1, dev = -1;
-        double *dblob = nullptr;
-        int *iblob = nullptr;
-        ~Scope() {
-            if (dblob) cudaFree(dblob);
-            if (iblob) cudaFree(iblob);
-            if (prev >= 0 && prev != dev) cudaSetDevice(prev);
-        }
+        ~Scope() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
     } scope;
     scope.dev = device;
     cudaGetDevice(&scope.prev);
@@ -354,10 +364,6 @@ static int batched_minimize_impl(int device, int64_t nbatch, int64_t nsite, cons
     // one device blob for the topology
     const size_t nd1 = std::max(nd, 1), np1 = std::max<size_t>(th_row.size(), 1);
     const size_t dbl = nsite + nd1 + nd1 + np1 + nsite, itg = nd1 + nsite + (nd + 1) + np1;
-    UPOL_CUDA(cudaMalloc((void **)&scope.dblob, dbl * sizeof(double)));
-    UPOL_CUDA(cudaMalloc((void **)&scope.iblob, itg * sizeof(int)));
-    double *dblob = scope.dblob;
-    int *iblob = scope.iblob;
     std::vector<double> hd;
     hd.insert(hd.end(), q_core, q_core + nsite);
     hd.insert(hd.end(), row_qs.begin(), row_qs.end()); hd.resize(nsite + nd1, 0.0);
@@ -369,8 +375,35 @@ static int batched_minimize_impl(int device, int64_t nbatch, int64_t nsite, cons
     hi.insert(hi.end(), site_mol.begin(), site_mol.end());
     hi.insert(hi.end(), th_ptr.begin(), th_ptr.end());
     hi.insert(hi.end(), th_row.begin(), th_row.end()); hi.resize(itg, 0);
-    UPOL_CUDA(cudaMemcpyAsync(dblob, hd.data(), dbl * sizeof(double), cudaMemcpyHostToDevice, st));
-    UPOL_CUDA(cudaMemcpyAsync(iblob, hi.data(), itg * sizeof(int), cudaMemcpyHostToDevice, st));
+    // The topology tables live on the device across calls (a scan driver calls this once per batch of conformers
+    // with the same force field): a small cache keyed by device and table contents; on a hit nothing is allocated
+    // or copied.  Entries are only freed on eviction (cudaFree waits for kernels that may still read them).
+    double *dblob = nullptr;
+    int *iblob = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_topo_mutex);
+        for (auto &c : g_topo_cache)
+            if (c.device == device && c.hd == hd && c.hi == hi) { dblob = c.dblob; iblob = c.iblob; c.stamp = ++g_topo_stamp; break; }
+        if (!dblob) {
+            if (g_topo_cache.size() >= 8) {
+                size_t old = 0;
+                for (size_t q = 1; q < g_topo_cache.size(); ++q) if (g_topo_cache[q].stamp < g_topo_cache[old].stamp) old = q;
+                cudaFree(g_topo_cache[old].dblob); cudaFree(g_topo_cache[old].iblob);
+                g_topo_cache.erase(g_topo_cache.begin() + old);
+            }
+            TopoEntry c;
+            c.device = device;
+            UPOL_CUDA(cudaMalloc((void **)&c.dblob, dbl * sizeof(double)));
+            if (cudaMalloc((void **)&c.iblob, itg * sizeof(int)) != cudaSuccess) { cudaFree(c.dblob); set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__); return UPOL_ERR_CUDA; }
+            cudaError_t ce = cudaMemcpy(c.dblob, hd.data(), dbl * sizeof(double), cudaMemcpyHostToDevice);
+            if (ce == cudaSuccess) ce = cudaMemcpy(c.iblob, hi.data(), itg * sizeof(int), cudaMemcpyHostToDevice);
+            if (ce == cudaSuccess) ce = cudaDeviceSynchronize();      // pageable copies on the legacy stream: landed before any stream reads them
+            if (ce != cudaSuccess) { cudaFree(c.dblob); cudaFree(c.iblob); set_last_cuda_error(ce, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
+            c.hd = hd; c.hi = hi; c.stamp = ++g_topo_stamp;
+            dblob = c.dblob; iblob = c.iblob;
+            g_topo_cache.push_back(std::move(c));
+        }
+    }
     BatchTopo t;
     t.nsite = (int)nsite; t.nd = nd; t.npairs = (int)th_row.size();
     t.qc = dblob; t.row_qs = dblob + nsite; t.row_k = dblob + nsite + nd1; t.th_u = dblob + nsite + 2 * nd1;
@@ -391,7 +424,7 @@ static int batched_minimize_impl(int device, int64_t nbatch, int64_t nsite, cons
     batched_bfgs_kernel<<<blocks, 32 * wpb, smem, st>>>(t, site_qs_dev, nbatch, r_core_dev, d_dev, tol, maxiter,
                                                        energy_dev, iterations_dev, wpb, per_warp);
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);     // the topology blobs die with `scope`
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);     // documented: returns after the batch has finished
     if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
     return UPOL_OK;
 }
