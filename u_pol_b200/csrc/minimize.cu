@@ -315,8 +315,9 @@ __device__ void control_body(int m, int mixed_enabled, int *__restrict__ ic, dou
     const double alpha = sc[D_ALPHA];
     if (first) {
         sc[D_GNORM0] = gnorm;
-        // mixed field error ~1.5e-6 of the gross field (= ||g(d=0)||).  Switching later (5e-5) was
-        // measured to cost one extra iteration at 100 k Drudes, so the switch stays at 1e-3.
+        // mixed field error ~1.5e-6 of the gross field (= ||g(d=0)||).  Hand-over swept in round 2
+        // (profiles/r02_variants_switch.txt): 1e-4 saves 4 % at 100 k Drudes and 3 % at 20 k against 1e-3; 3e-5 and
+        // below start to cost a 14th iteration at 100 k Drudes and leave less than 20x head-room over the noise.
         sc[D_SWITCH] = sc[D_SWITCH_REL] * gnorm;
         accept = true;
     } else {
@@ -745,7 +746,7 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
         build_blocks_kernel<<<(unsigned)((s->mol_hi - s->mol_lo + 63) / 64), 64, 0, st>>>(
             (int)s->mol_lo, (int)s->mol_hi, w->mol_row0, w->mol_nrow, w->blk_off, s->row_site, s->r, s->row_qs,
             s->row_k, s->th_ptr, s->th_row, s->th_u, w->blk);
-    static const double switch_rel = getenv("UPOL_MIXED_SWITCH") ? atof(getenv("UPOL_MIXED_SWITCH")) : 1e-3;
+    static const double switch_rel = getenv("UPOL_MIXED_SWITCH") ? atof(getenv("UPOL_MIXED_SWITCH")) : 1e-4;
     init_state_kernel<<<1, 1, 0, st>>>(w->ic, w->sc, o->tol, mixed ? kGatePhaseMixed : kGatePhase64, o->maxiter, switch_rel);
     UPOL_CUDA(cudaMemsetAsync(w->S, 0, sizeof(double) * (size_t)std::max(m, 1) * std::max<int64_t>(n, 1), st));
     UPOL_CUDA(cudaMemsetAsync(w->Y, 0, sizeof(double) * (size_t)std::max(m, 1) * std::max<int64_t>(n, 1), st));

@@ -686,26 +686,47 @@ int sys_ensure_hscratch(upol_system *s, size_t elems) {
     return UPOL_OK;
 }
 
-// Bounding box of the positions (one block; used by the device-pointer set_positions path).
-__global__ void bbox_kernel(int nsite, const double *__restrict__ r, double *__restrict__ out6) {
-    __shared__ double lo[3][32], hi[3][32];
+// Bounding box of the positions: every block reduces its stripe, the block that finishes last folds the block
+// results (a single block took 110 us for 180 000 sites, 2 % of an 8-GPU end-to-end step).
+__global__ void __launch_bounds__(256)
+bbox_kernel(int nsite, const double *__restrict__ r, double *__restrict__ partial, int *__restrict__ ticket, double *__restrict__ out6) {
+    __shared__ double lo[3][8], hi[3][8];
+    __shared__ int is_last;
     double l[3] = {1e300, 1e300, 1e300}, h[3] = {-1e300, -1e300, -1e300};
-    for (int i = threadIdx.x; i < nsite; i += blockDim.x)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nsite; i += gridDim.x * blockDim.x)
         for (int c = 0; c < 3; ++c) { const double v = r[3 * i + c]; l[c] = fmin(l[c], v); h[c] = fmax(h[c], v); }
-    for (int c = 0; c < 3; ++c) {
-        for (int o = 16; o > 0; o >>= 1) {
-            l[c] = fmin(l[c], __shfl_down_sync(0xffffffffu, l[c], o));
-            h[c] = fmax(h[c], __shfl_down_sync(0xffffffffu, h[c], o));
+    auto block_reduce = [&]() {
+        for (int c = 0; c < 3; ++c) {
+            for (int o = 16; o > 0; o >>= 1) {
+                l[c] = fmin(l[c], __shfl_down_sync(0xffffffffu, l[c], o));
+                h[c] = fmax(h[c], __shfl_down_sync(0xffffffffu, h[c], o));
+            }
+            if ((threadIdx.x & 31) == 0) { lo[c][threadIdx.x >> 5] = l[c]; hi[c][threadIdx.x >> 5] = h[c]; }
         }
-        if ((threadIdx.x & 31) == 0) { lo[c][threadIdx.x >> 5] = l[c]; hi[c][threadIdx.x >> 5] = h[c]; }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int c = 0; c < 3; ++c) {
+                for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo[c][0] = fmin(lo[c][0], lo[c][w]); hi[c][0] = fmax(hi[c][0], hi[c][w]); }
+            }
+        __syncthreads();
+    };
+    block_reduce();
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 3; ++c) { partial[6 * blockIdx.x + c] = lo[c][0]; partial[6 * blockIdx.x + 3 + c] = hi[c][0]; }
+        __threadfence();
+        is_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
-    if (threadIdx.x == 0)
-        for (int c = 0; c < 3; ++c) {
-            double a = lo[c][0], b = hi[c][0];
-            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = fmin(a, lo[c][w]); b = fmax(b, hi[c][w]); }
-            out6[c] = a; out6[3 + c] = b;
-        }
+    if (!is_last) return;
+    __threadfence();
+    for (int c = 0; c < 3; ++c) { l[c] = 1e300; h[c] = -1e300; }
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+        for (int c = 0; c < 3; ++c) { l[c] = fmin(l[c], __ldcg(partial + 6 * b + c)); h[c] = fmax(h[c], __ldcg(partial + 6 * b + 3 + c)); }
+    block_reduce();
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 3; ++c) { out6[c] = lo[c][0]; out6[3 + c] = hi[c][0]; }
+        *ticket = 0;
+    }
 }
 
 void set_box(upol_system *s, const double *lo, const double *hi) {
@@ -722,7 +743,8 @@ void set_box(upol_system *s, const double *lo, const double *hi) {
 }
 
 int sys_box_from_device(upol_system *s, cudaStream_t st) {
-    bbox_kernel<<<1, 1024, 0, st>>>((int)s->nsite, s->r, s->eblock);
+    const unsigned nbb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(148, (s->nsite + 2047) / 2048));
+    bbox_kernel<<<nbb, 256, 0, st>>>((int)s->nsite, s->r, s->part, s->ticket + 1, s->eblock);
     double h[6];
     UPOL_CUDA(cudaMemcpyAsync(h, s->eblock, sizeof(h), cudaMemcpyDeviceToHost, st));
     UPOL_CUDA(cudaStreamSynchronize(st));
