@@ -11,6 +11,9 @@ sysm = UindSystem.from_drude_system(s)
 e, g = sysm.energy_grad(D)
 em, gm = sysm.energy_grad(D, precision="mixed")
 eh, gh = sysm.energy_grad_host(D)
+es, gs, rng = sysm.energy_grad_host_sharded(np.asarray(D).reshape(-1), r_core=np.ascontiguousarray(s.r_core.reshape(-1)))
+sysm.energy_grad(D, want_energy=False); sysm.energy_grad(D, precision="mixed", want_energy=False)
+cg = sysm.core_gradient(D)
 sysm.set_row_range(3, 17); sysm.energy_grad(D); sysm.set_row_range(0, 30)
 d, info = sysm.minimize(tol=1e-5)
 d2, info2 = sysm.minimize(tol=1e-5, precision="mixed", method="cg")

@@ -235,3 +235,24 @@ def test_dense_wrappers_reuse_the_device_system():
     assert us == pytest.approx(0.5 * float((np.asarray(k).reshape(-1, 1) * d_opt.cpu().numpy().reshape(-1, 3) ** 2).sum()), rel=1e-12)
     pol.clear_cache()
     assert not pol._CACHE
+
+
+def test_sharded_host_entry_single_rank_pageable_and_pinned_buffers():
+    """upol_uind_energy_grad_host_sharded with one rank = set_positions + energy_grad_host in one call; pageable
+    numpy buffers are staged through the library's own page-locked memory, page-locked ones are used directly."""
+    import torch
+
+    s = synth.imidazole_box(40, seed=21)
+    D = synth.random_displacements(s, seed=22)
+    sysm = UindSystem.from_drude_system(s)
+    e_ref, g_ref = sysm.energy_grad(D)
+    r2 = s.r_core + 0.013                                  # a translated copy: same energy, new geometry upload
+    for pinned in (False, True):
+        mk = (lambda a: torch.from_numpy(np.ascontiguousarray(a.reshape(-1))).pin_memory().numpy()) if pinned else \
+             (lambda a: np.ascontiguousarray(a.reshape(-1)))
+        e, g, (lo, hi) = sysm.energy_grad_host_sharded(mk(np.asarray(D)), r_core=mk(r2))
+        assert (lo, hi) == (0, s.nmol * s.natoms)
+        assert abs(e[0] - float(e_ref[0])) <= 1e-10 * abs(float(e_ref[0]))
+        assert np.abs(g - g_ref.cpu().numpy()).max() <= 1e-10 * float(g_ref.abs().max())
+        em, gm, _ = sysm.energy_grad_host_sharded(mk(np.asarray(D)), precision="mixed")     # geometry kept
+        assert abs(em[0] - float(e_ref[0])) <= 1e-5 * abs(float(e_ref[0]))

@@ -376,13 +376,13 @@ static int upol_uind_energy_grad_host_sharded_impl(upol_system *s, const double 
     if (site_lo_out) *site_lo_out = lo;
     if (site_hi_out) *site_hi_out = hi;
     const size_t n3 = 3 * (size_t)s->nsite, m3 = 3 * (size_t)(hi - lo), o3 = 3 * (size_t)lo;
-    rc = sys_ensure_pinned(s, sizeof(double) * (2 * n3 + UPOL_E_SIZE));
+    rc = sys_ensure_pinned(s, sizeof(double) * (3 * n3 + UPOL_E_SIZE));      // staging for r, d, grad slices + energy
     if (rc) return rc;
     rc = sys_ensure_hscratch(s, 2 * n3 + UPOL_E_SIZE);
     if (rc) return rc;
     if (!s->xd) UPOL_CUDA(cudaMalloc((void **)&s->xd, sizeof(double) * n3));      // single rank / NCCL-only runs
     double *gfull = s->hscratch + n3, *e_dev = gfull + n3;
-    double *pr = s->pin, *pd = s->pin + m3, *pg = s->pin + 2 * m3, *pe = s->pin + 2 * n3;
+    double *pr = s->pin, *pd = s->pin + m3, *pg = s->pin + 2 * m3, *pe = s->pin + 3 * n3;
     cudaStream_t st = 0;
     // only this rank's site slices of r and d cross PCIe; the peers' slices arrive over NVLink
     if (r_core) {
@@ -428,7 +428,7 @@ int upol_uind_energy_grad_host(upol_system *s, const double *d, int precision, d
     if (!s || !d || (!energy && !grad)) return UPOL_ERR_ARG;
     DeviceGuard guard(s->device);
     const size_t n3 = 3 * (size_t)s->nsite;
-    int rc = sys_ensure_pinned(s, sizeof(double) * (2 * n3 + UPOL_E_SIZE));
+    int rc = sys_ensure_pinned(s, sizeof(double) * (3 * n3 + UPOL_E_SIZE));      // staging for r, d, grad slices + energy
     if (rc) return rc;
     rc = sys_ensure_hscratch(s, 2 * n3 + UPOL_E_SIZE);
     if (rc) return rc;
@@ -543,7 +543,7 @@ int upol_minimize_host(upol_system *s, double *d, const upol_min_options *opts, 
     if (!s || !d || !res) return UPOL_ERR_ARG;
     DeviceGuard guard(s->device);
     const size_t n3 = 3 * (size_t)s->nsite;
-    int rc = sys_ensure_pinned(s, sizeof(double) * (2 * n3 + UPOL_E_SIZE));
+    int rc = sys_ensure_pinned(s, sizeof(double) * (3 * n3 + UPOL_E_SIZE));      // staging for r, d, grad slices + energy
     if (rc) return rc;
     rc = sys_ensure_hscratch(s, 2 * n3 + UPOL_E_SIZE);
     if (rc) return rc;
