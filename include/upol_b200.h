@@ -281,6 +281,11 @@ int upol_system_kernel_time(upol_system *sys, double *ms_total, int32_t *launche
 int upol_system_set_periodic(upol_system *sys, const double *box, double kappa, int32_t nmax);
 int upol_system_periodic_info(upol_system *sys, double *box3, double *kappa, int32_t *n_kvectors);
 
+/* Debug aid (compute-sanitizer stand-in): with UPOL_GUARD=1 in the environment every device buffer of the library
+ * carries guard zones; this returns the number of damaged ones over all live buffers (0 = clean, -1 = guard mode off). */
+int upol_debug_check_guards(void);
+int upol_debug_guard_selftest(void);   /* 1 = a deliberate one-byte overrun was detected */
+
 /* FMA-pipe peak microbenchmarks used as roofline denominators: returns the
  * measured FLOP/s of a register-resident FMA chain on the current device: use_fp64 = 1 fp64 (DFMA),
  * 0 fp32 (FFMA), 2 packed fp32 pairs (FFMA2, fma.rn.f32x2). */

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "upol_system_set_kernel_timing": (C.c_int, [_P, C.c_int]),
     "upol_system_launch_count": (_I64, [_P]),
     "upol_system_kernel_time": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "upol_debug_check_guards": (C.c_int, []),
+    "upol_debug_guard_selftest": (C.c_int, []),
     "upol_measure_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "upol_system_set_periodic": (C.c_int, [_P, _P, C.c_double, C.c_int32]),
     "upol_system_periodic_info": (C.c_int, [_P, _P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),

@@ -29,7 +29,7 @@ template <typename T>
 int dev_alloc(T **p, size_t n) {
     *p = nullptr;
     if (n == 0) n = 1;
-    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    cudaError_t e = upol::dmalloc((void **)p, n * sizeof(T));
     if (e != cudaSuccess) { set_last_cuda_error(e, __FILE__, __LINE__); return UPOL_ERR_ALLOC; }
     return UPOL_OK;
 }
@@ -45,9 +45,9 @@ void free_system(upol_system *s) {
                     s->gc, s->eblock, s->energy, s->e_static, s->phi_static, s->site_row,
                     s->cols_dcore, s->site_x, s->exS_lo, s->cf_tmp,
                     s->cols_x, s->cols_d, s->cols_d2, s->col_qeff, s->ticket, s->site_nslot, s->exP_lo, s->exP_len, s->exN_lo, s->exN_len};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : ptrs) if (p) upol::dfree(p);
     if (s->pin) cudaFreeHost(s->pin);
-    if (s->hscratch) cudaFree(s->hscratch);
+    if (s->hscratch) upol::dfree(s->hscratch);
     for (cudaEvent_t e : s->tev) cudaEventDestroy(e);
     delete s;
 }
@@ -380,7 +380,7 @@ static int upol_uind_energy_grad_host_sharded_impl(upol_system *s, const double 
     if (rc) return rc;
     rc = sys_ensure_hscratch(s, 2 * n3 + UPOL_E_SIZE);
     if (rc) return rc;
-    if (!s->xd) UPOL_CUDA(cudaMalloc((void **)&s->xd, sizeof(double) * n3));      // single rank / NCCL-only runs
+    if (!s->xd) UPOL_CUDA(upol::dmalloc((void **)&s->xd, sizeof(double) * n3));      // single rank / NCCL-only runs
     double *gfull = s->hscratch + n3, *e_dev = gfull + n3;
     double *pr = s->pin, *pd = s->pin + m3, *pg = s->pin + 2 * m3, *pe = s->pin + 3 * n3;
     cudaStream_t st = 0;

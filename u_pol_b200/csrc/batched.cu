@@ -388,17 +388,17 @@ static int batched_minimize_impl(int device, int64_t nbatch, int64_t nsite, cons
             if (g_topo_cache.size() >= 8) {
                 size_t old = 0;
                 for (size_t q = 1; q < g_topo_cache.size(); ++q) if (g_topo_cache[q].stamp < g_topo_cache[old].stamp) old = q;
-                cudaFree(g_topo_cache[old].dblob); cudaFree(g_topo_cache[old].iblob);
+                upol::dfree(g_topo_cache[old].dblob); upol::dfree(g_topo_cache[old].iblob);
                 g_topo_cache.erase(g_topo_cache.begin() + old);
             }
             TopoEntry c;
             c.device = device;
-            UPOL_CUDA(cudaMalloc((void **)&c.dblob, dbl * sizeof(double)));
-            if (cudaMalloc((void **)&c.iblob, itg * sizeof(int)) != cudaSuccess) { cudaFree(c.dblob); set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__); return UPOL_ERR_CUDA; }
+            UPOL_CUDA(upol::dmalloc((void **)&c.dblob, dbl * sizeof(double)));
+            if (upol::dmalloc((void **)&c.iblob, itg * sizeof(int)) != cudaSuccess) { upol::dfree(c.dblob); set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__); return UPOL_ERR_CUDA; }
             cudaError_t ce = cudaMemcpy(c.dblob, hd.data(), dbl * sizeof(double), cudaMemcpyHostToDevice);
             if (ce == cudaSuccess) ce = cudaMemcpy(c.iblob, hi.data(), itg * sizeof(int), cudaMemcpyHostToDevice);
             if (ce == cudaSuccess) ce = cudaDeviceSynchronize();      // pageable copies on the legacy stream: landed before any stream reads them
-            if (ce != cudaSuccess) { cudaFree(c.dblob); cudaFree(c.iblob); set_last_cuda_error(ce, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
+            if (ce != cudaSuccess) { upol::dfree(c.dblob); upol::dfree(c.iblob); set_last_cuda_error(ce, __FILE__, __LINE__); return UPOL_ERR_CUDA; }
             c.hd = hd; c.hi = hi; c.stamp = ++g_topo_stamp;
             dblob = c.dblob; iblob = c.iblob;
             g_topo_cache.push_back(std::move(c));

@@ -122,7 +122,7 @@ void p2p_destroy(upol_system *s) {
     s->ipc_opened.clear();
     void *ptrs[] = {s->xchg_pack, s->xchg_flags, s->d_peer_x, s->d_peer_pack, s->d_peer_flags,
                     s->xg, s->xe, s->xd, s->xflags2, s->d_peer_g, s->d_peer_e, s->d_peer_r, s->d_peer_d, s->d_peer_flags2};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : ptrs) if (p) dfree(p);      // xd may come from the guarded allocator (single-rank sharded host path)
     s->xchg_pack = nullptr; s->xchg_flags = nullptr;
     s->d_peer_x = nullptr; s->d_peer_pack = nullptr; s->d_peer_flags = nullptr;
     s->xg = nullptr; s->xe = nullptr; s->xd = nullptr; s->xflags2 = nullptr;
@@ -273,6 +273,7 @@ extern "C" int upol_system_attach_comm(upol_system *s, const unsigned char *id_b
 // ---- peer-memory exchange (CUDA IPC over NVLink) -------------------------------------------------
 extern "C" int upol_system_p2p_export(upol_system *s, unsigned char *blob) {
     if (!s || !blob || s->nranks < 2 || s->nranks > 32) return UPOL_ERR_ARG;   // one warp polls the peers' flags
+    if (guard_enabled()) return UPOL_ERR_ARG;                                  // guarded buffers cannot be IPC-exported (guard.cu)
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(s->device);

@@ -39,6 +39,11 @@ void set_last_cuda_error(cudaError_t e, const char *file, int line);
 
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
+// device allocations of the library (guard.cu): plain cudaMalloc / cudaFree unless UPOL_GUARD=1
+cudaError_t dmalloc(void **p, size_t bytes);
+cudaError_t dfree(void *p);
+bool guard_enabled();
+
 // Arguments of one pair-kernel launch (struct passed by value).
 struct PairArgs {
     // rows

@@ -400,7 +400,7 @@ void ewald_free(upol_system *s) {
     EwaldState *e = static_cast<EwaldState *>(s->ewald);
     if (!e) return;
     void *ptrs[] = {e->kn, e->kA, e->Sc, e->Ss0, e->Ssd, e->Sstat, e->Szero, e->cols0, e->rec, e->partial, e->mol_site0, e->mol_nsite, e->bad};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : ptrs) if (p) upol::dfree(p);
     delete e;
     s->ewald = nullptr;
 }
@@ -459,19 +459,19 @@ int ewald_setup(upol_system *s, const double *box, double kappa, int nmax) {
     kn.resize(e->nk_pad, make_int4(0, 0, 0, 0));
     kA.resize(e->nk_pad, 0.0);
     auto fail = [&](int rc) { ewald_free(s); return rc; };
-    if (cudaMalloc((void **)&e->kn, sizeof(int4) * e->nk_pad) != cudaSuccess ||
-        cudaMalloc((void **)&e->kA, sizeof(double) * e->nk_pad) != cudaSuccess ||
-        cudaMalloc((void **)&e->Sc, sizeof(double2) * e->nk_pad) != cudaSuccess ||
-        cudaMalloc((void **)&e->Ss0, sizeof(double2) * e->nk_pad) != cudaSuccess ||
-        cudaMalloc((void **)&e->Ssd, sizeof(double2) * e->nk_pad) != cudaSuccess ||
-        cudaMalloc((void **)&e->Sstat, sizeof(double2) * e->nk_pad) != cudaSuccess ||
-        cudaMalloc((void **)&e->Szero, sizeof(double2) * e->nk_pad) != cudaSuccess ||
-        cudaMalloc((void **)&e->cols0, sizeof(double4) * std::max<int64_t>(s->nb_pad, 1)) != cudaSuccess ||
-        cudaMalloc((void **)&e->rec, sizeof(double2) * 3 * std::max<int64_t>(std::max(s->na_pad, s->nb_pad), 1)) != cudaSuccess ||
-        cudaMalloc((void **)&e->partial, sizeof(double2) * (size_t)kSfacChunks * e->nk_pad) != cudaSuccess ||
-        cudaMalloc((void **)&e->mol_site0, sizeof(int) * std::max<int64_t>(s->nmol, 1)) != cudaSuccess ||
-        cudaMalloc((void **)&e->mol_nsite, sizeof(int) * std::max<int64_t>(s->nmol, 1)) != cudaSuccess ||
-        cudaMalloc((void **)&e->bad, sizeof(int)) != cudaSuccess) {
+    if (upol::dmalloc((void **)&e->kn, sizeof(int4) * e->nk_pad) != cudaSuccess ||
+        upol::dmalloc((void **)&e->kA, sizeof(double) * e->nk_pad) != cudaSuccess ||
+        upol::dmalloc((void **)&e->Sc, sizeof(double2) * e->nk_pad) != cudaSuccess ||
+        upol::dmalloc((void **)&e->Ss0, sizeof(double2) * e->nk_pad) != cudaSuccess ||
+        upol::dmalloc((void **)&e->Ssd, sizeof(double2) * e->nk_pad) != cudaSuccess ||
+        upol::dmalloc((void **)&e->Sstat, sizeof(double2) * e->nk_pad) != cudaSuccess ||
+        upol::dmalloc((void **)&e->Szero, sizeof(double2) * e->nk_pad) != cudaSuccess ||
+        upol::dmalloc((void **)&e->cols0, sizeof(double4) * std::max<int64_t>(s->nb_pad, 1)) != cudaSuccess ||
+        upol::dmalloc((void **)&e->rec, sizeof(double2) * 3 * std::max<int64_t>(std::max(s->na_pad, s->nb_pad), 1)) != cudaSuccess ||
+        upol::dmalloc((void **)&e->partial, sizeof(double2) * (size_t)kSfacChunks * e->nk_pad) != cudaSuccess ||
+        upol::dmalloc((void **)&e->mol_site0, sizeof(int) * std::max<int64_t>(s->nmol, 1)) != cudaSuccess ||
+        upol::dmalloc((void **)&e->mol_nsite, sizeof(int) * std::max<int64_t>(s->nmol, 1)) != cudaSuccess ||
+        upol::dmalloc((void **)&e->bad, sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
         return fail(UPOL_ERR_ALLOC);
     }

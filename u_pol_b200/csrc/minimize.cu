@@ -81,7 +81,7 @@ void ws_free(MinWs *w) {
     if (!w) return;
     void *ptrs[] = {w->x0, w->g0, w->p, w->g, w->Pg, w->Py, w->S, w->Y, w->partial, w->pack, w->sc, w->ic,
                     w->coef, w->RS, w->YY, w->e_final, w->blk, w->blk_off, w->mol_row0, w->mol_nrow, w->row_mol};
-    for (void *q : ptrs) if (q) cudaFree(q);
+    for (void *q : ptrs) if (q) upol::dfree(q);
     if (w->h_ic) cudaFreeHost(w->h_ic);
     if (w->h_sc) cudaFreeHost(w->h_sc);
     for (auto &e : w->ev) if (e) cudaEventDestroy(e);
@@ -664,13 +664,13 @@ static int ws_ensure(upol_system *s, int m, MinWs **out) {
     w->m = m; w->n = n;
     const int64_t nn = std::max<int64_t>(n, 1);
     w->nblocks = (int)std::min<int64_t>(148 * 2, (nn + kDotBlock - 1) / kDotBlock);
-    auto A = [&](double **p, size_t cnt) { return cudaMalloc((void **)p, sizeof(double) * std::max<size_t>(cnt, 1)) == cudaSuccess; };
+    auto A = [&](double **p, size_t cnt) { return upol::dmalloc((void **)p, sizeof(double) * std::max<size_t>(cnt, 1)) == cudaSuccess; };
     bool ok = A(&w->x0, nn) && A(&w->g0, nn) && A(&w->p, nn) && A(&w->g, nn) && A(&w->Pg, nn) && A(&w->Py, nn) &&
               A(&w->S, (size_t)std::max(m, 1) * nn) && A(&w->Y, (size_t)std::max(m, 1) * nn) &&
               A(&w->partial, (size_t)w->nblocks * (m + 1) * kDotVals) && A(&w->pack, (size_t)(m + 1) * kDotVals) &&
               A(&w->sc, D_SIZE) && A(&w->coef, 2 * kMaxHist) && A(&w->RS, (size_t)std::max(m * m, 1)) &&
               A(&w->YY, (size_t)std::max(m * m, 1)) && A(&w->e_final, UPOL_E_SIZE);
-    ok = ok && cudaMalloc((void **)&w->ic, sizeof(int) * I_SIZE) == cudaSuccess;
+    ok = ok && upol::dmalloc((void **)&w->ic, sizeof(int) * I_SIZE) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&w->h_ic, sizeof(int) * I_SIZE * 2) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&w->h_sc, sizeof(double) * D_SIZE * 2) == cudaSuccess;
     for (auto &e : w->ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
@@ -690,10 +690,10 @@ static int ws_ensure(upol_system *s, int m, MinWs **out) {
         }
         w->blk_elems = std::max<int64_t>(tot, 1);
         ok = ok && A(&w->blk, (size_t)w->blk_elems);
-        ok = ok && cudaMalloc((void **)&w->blk_off, sizeof(int64_t) * off.size()) == cudaSuccess;
-        ok = ok && cudaMalloc((void **)&w->mol_row0, sizeof(int) * off.size()) == cudaSuccess;
-        ok = ok && cudaMalloc((void **)&w->mol_nrow, sizeof(int) * off.size()) == cudaSuccess;
-        ok = ok && cudaMalloc((void **)&w->row_mol, sizeof(int) * rmol.size()) == cudaSuccess;
+        ok = ok && upol::dmalloc((void **)&w->blk_off, sizeof(int64_t) * off.size()) == cudaSuccess;
+        ok = ok && upol::dmalloc((void **)&w->mol_row0, sizeof(int) * off.size()) == cudaSuccess;
+        ok = ok && upol::dmalloc((void **)&w->mol_nrow, sizeof(int) * off.size()) == cudaSuccess;
+        ok = ok && upol::dmalloc((void **)&w->row_mol, sizeof(int) * rmol.size()) == cudaSuccess;
         if (ok && s->nmol > 0) {
             ok = ok && cudaMemcpy(w->blk_off, off.data(), sizeof(int64_t) * s->nmol, cudaMemcpyHostToDevice) == cudaSuccess;
             ok = ok && cudaMemcpy(w->mol_row0, s->h_mol_row0.data(), sizeof(int) * s->nmol, cudaMemcpyHostToDevice) == cudaSuccess;

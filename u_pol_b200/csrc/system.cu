@@ -679,9 +679,9 @@ int sys_ensure_pinned(upol_system *s, size_t bytes) {
 
 int sys_ensure_hscratch(upol_system *s, size_t elems) {
     if (s->hscratch_elems >= elems) return UPOL_OK;
-    if (s->hscratch) cudaFree(s->hscratch);
+    if (s->hscratch) upol::dfree(s->hscratch);
     s->hscratch = nullptr; s->hscratch_elems = 0;
-    UPOL_CUDA(cudaMalloc((void **)&s->hscratch, sizeof(double) * elems));
+    UPOL_CUDA(upol::dmalloc((void **)&s->hscratch, sizeof(double) * elems));
     s->hscratch_elems = elems;
     return UPOL_OK;
 }
@@ -838,18 +838,18 @@ int sys_coulomb_static(upol_system *s, double *out2, cudaStream_t st) {
         double *rows = nullptr, *part = nullptr, *eblock = nullptr;
         int *ex = nullptr;
         double4 *cols = nullptr;
-        ~Scratch() { cudaFree(rows); cudaFree(part); cudaFree(eblock); cudaFree(ex); cudaFree(cols); }
+        ~Scratch() { upol::dfree(rows); upol::dfree(part); upol::dfree(eblock); upol::dfree(ex); upol::dfree(cols); }
     } sc;
     const int ntile = (int)(s->na_pad / kTileCols);
     const int64_t rb = (n + kRowTile - 1) / kRowTile;
     int split = (int)std::max<int64_t>(1, std::min<int64_t>(ntile, (148 * 8 + rb - 1) / rb));
     const int64_t stride = part_stride_for(n);
     const int nb = (int)nblk(n, kFinRows);
-    UPOL_CUDA(cudaMalloc((void **)&sc.rows, sizeof(double) * 3 * n));
-    UPOL_CUDA(cudaMalloc((void **)&sc.ex, sizeof(int) * 4 * n));
-    UPOL_CUDA(cudaMalloc((void **)&sc.cols, sizeof(double4) * s->na_pad));
-    UPOL_CUDA(cudaMalloc((void **)&sc.part, sizeof(double) * split * kPartComps * stride));
-    UPOL_CUDA(cudaMalloc((void **)&sc.eblock, sizeof(double) * nb));
+    UPOL_CUDA(upol::dmalloc((void **)&sc.rows, sizeof(double) * 3 * n));
+    UPOL_CUDA(upol::dmalloc((void **)&sc.ex, sizeof(int) * 4 * n));
+    UPOL_CUDA(upol::dmalloc((void **)&sc.cols, sizeof(double4) * s->na_pad));
+    UPOL_CUDA(upol::dmalloc((void **)&sc.part, sizeof(double) * split * kPartComps * stride));
+    UPOL_CUDA(upol::dmalloc((void **)&sc.eblock, sizeof(double) * nb));
     double *rows = sc.rows, *part = sc.part, *eblock = sc.eblock;
     int *ex = sc.ex;
     double4 *cols = sc.cols;
@@ -957,12 +957,12 @@ int sys_core_forces(upol_system *s, const double *dcmp, double *dudr, cudaStream
     const int64_t n = s->nsite, nd = s->nd;
     if (!s->cf_tmp) {      // first use: tables of the site-row pass
         s->ns_pad = round_up(n, 512);
-        UPOL_CUDA(cudaMalloc((void **)&s->cols_dcore, sizeof(double4) * s->nb_pad));
-        UPOL_CUDA(cudaMalloc((void **)&s->site_x, sizeof(double) * 3 * s->ns_pad));
+        UPOL_CUDA(upol::dmalloc((void **)&s->cols_dcore, sizeof(double4) * s->nb_pad));
+        UPOL_CUDA(upol::dmalloc((void **)&s->site_x, sizeof(double) * 3 * s->ns_pad));
         s->site_y = s->site_x + s->ns_pad; s->site_z = s->site_y + s->ns_pad;
-        UPOL_CUDA(cudaMalloc((void **)&s->exS_lo, sizeof(int) * 3 * s->ns_pad));
+        UPOL_CUDA(upol::dmalloc((void **)&s->exS_lo, sizeof(int) * 3 * s->ns_pad));
         s->exS_len = s->exS_lo + s->ns_pad; s->exS2_lo = s->exS_len + s->ns_pad;
-        UPOL_CUDA(cudaMalloc((void **)&s->cf_tmp, sizeof(double) * (6 * std::max<int64_t>(nd, 1) + 6 * n)));
+        UPOL_CUDA(upol::dmalloc((void **)&s->cf_tmp, sizeof(double) * (6 * std::max<int64_t>(nd, 1) + 6 * n)));
         std::vector<int> ex(3 * s->ns_pad, 0);
         for (int64_t j = 0; j < n; ++j) {
             const int m = s->h_mol[j];
