@@ -39,6 +39,16 @@ for case in range(n_cases):
     dE = abs(float(e2[0]) - float(e1[0])) / scale
     gmax = float(g1.abs().max())
     dg = float((g2 - g1).abs().max()) / gmax if gmax > 0 else float((g2 - g1).abs().max())
+    # sharded host path (only this rank's slices cross PCIe) and a mixed call through the same exchange
+    nsite = g1.shape[0]
+    r_host = np.ascontiguousarray(np.asarray(full._keep[0]).reshape(-1)); d_host = np.ascontiguousarray(np.asarray(D, dtype=np.float64).reshape(-1))
+    eh, gh, (slo, shi) = sh.energy_grad_host_sharded(d_host, r_core=r_host if case % 4 < 2 else None)
+    gt = torch.as_tensor(gh).to(g1.device); dist.all_reduce(gt)
+    dE = max(dE, abs(eh[0] - float(e1[0])) / scale)
+    dg = max(dg, float((gt - g1).abs().max()) / (gmax if gmax > 0 else 1.0))
+    em, gm = sh.energy_grad(D, precision="mixed")
+    if abs(float(em[0]) - float(e1[0])) > 1e-5 * scale + 1e-9 * abs(float(e1[5])) or (gmax > 0 and float((gm - g1).abs().max()) > 1e-5 * gmax):
+        dE = max(dE, 1.0)      # counted as a failure below
     _, i1 = full.minimize(tol=1e-5); _, i2 = sh.minimize(tol=1e-5)
     dmin = 0.0
     if i1["flags"] == 0 and i2["flags"] == 0 and i1["U_ind"] != 0.0:
