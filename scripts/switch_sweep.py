@@ -15,4 +15,4 @@ for cfg in (3, 4):
         _, info = sysm.minimize(tol=1e-4, precision=prec)
         torch.cuda.synchronize(); t = time.perf_counter() - t0
         out.append(f"{prec} {t*1e3:8.2f} ms it {info['iterations']} ev {info['evaluations']} U {info['U_ind']:.9f} g {info['gnorm']:.2e} fl {info['flags']}")
-    print(f"switch {os.environ.get('UPOL_MIXED_SWITCH', '1e-3')} config {cfg}: " + " | ".join(out), flush=True)
+    print(f"switch {os.environ.get('UPOL_MIXED_SWITCH', '1e-4 (default)')} config {cfg}: " + " | ".join(out), flush=True)

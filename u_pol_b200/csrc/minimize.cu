@@ -57,6 +57,7 @@ struct MinWs {
     int *mol_row0 = nullptr, *mol_nrow = nullptr, *row_mol = nullptr;
     int64_t blk_elems = 0;
     int64_t nmol = 0;
+    int max_rows = 0;                        // Drude rows of the largest molecule
     double *partial = nullptr;               // [nblocks][(m+1)*kDotVals]
     double *pack = nullptr;                  // [(m+1)*kDotVals]
     double *sc = nullptr;                    // [D_SIZE]
@@ -146,6 +147,80 @@ __global__ void build_blocks_kernel(int mol_lo, int mol_hi, const int *__restric
             const double k = row_k[r0 + a];
             for (int c = 0; c < 3; ++c) A[(3 * a + c) * nb + 3 * a + c] = k > 0.0 ? 1.0 / k : 1.0;
         }
+    }
+}
+
+// The same, one WARP per molecule with the block in shared memory (3 nrow <= 32): lane j owns column j, so a
+// Gauss-Jordan sweep is 3 nrow row operations instead of (3 nrow)^2 element operations of one thread in global
+// memory (1.16 ms -> tens of microseconds for 20 000 imidazoles).  Identical arithmetic per element, identical result.
+constexpr int kBlkWarps = 4;
+__global__ void __launch_bounds__(32 * kBlkWarps)
+build_blocks_warp_kernel(int mol_lo, int mol_hi, const int *__restrict__ mol_row0,
+                         const int *__restrict__ mol_nrow, const int64_t *__restrict__ blk_off,
+                         const int *__restrict__ row_site, const double *__restrict__ r,
+                         const double *__restrict__ row_qs, const double *__restrict__ row_k,
+                         const int *__restrict__ th_ptr, const int *__restrict__ th_row,
+                         const double *__restrict__ th_u, double *__restrict__ blk) {
+    __shared__ double sm[kBlkWarps][32][33];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = mol_lo + blockIdx.x * kBlkWarps + wid;
+    if (m >= mol_hi) return;
+    const int r0 = mol_row0[m], nr = mol_nrow[m], nb = 3 * nr;
+    if (nr == 0) return;
+    double (*A)[33] = sm[wid];
+    for (int i = 0; i < nb; ++i) if (lane < nb) A[i][lane] = 0.0;
+    __syncwarp();
+    int coupled = 0;
+    if (lane < nr) {                                   // lane a fills the three rows of Drude a
+        const int a = lane;
+        const double k = row_k[r0 + a];
+        for (int c = 0; c < 3; ++c) A[3 * a + c][3 * a + c] = k > 0.0 ? k : 1.0;
+        const int sa = row_site[r0 + a];
+        for (int q = th_ptr[r0 + a]; q < th_ptr[r0 + a + 1]; ++q) {
+            const int b = th_row[q] - r0, sb = row_site[th_row[q]];
+            double G[3][3];
+            thole_hessian(r[3 * sb] - r[3 * sa], r[3 * sb + 1] - r[3 * sa + 1], r[3 * sb + 2] - r[3 * sa + 2], th_u[q], G);
+            const double qq = -kCoulomb * row_qs[r0 + a] * row_qs[r0 + b];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) A[3 * a + i][3 * b + j] = qq * G[i][j];
+            coupled = 1;
+        }
+    }
+    coupled = __any_sync(0xffffffffu, coupled);
+    __syncwarp();
+    bool ok = true;
+    if (coupled) {
+        for (int c = 0; c < nb; ++c) {                 // in-place Gauss-Jordan inverse, lane = column
+            const double piv = A[c][c];
+            if (!(piv > 0.0)) { ok = false; break; }   // uniform across the warp (shared value)
+            const double ip = 1.0 / piv;
+            __syncwarp();
+            if (lane == c) A[c][c] = 1.0;
+            __syncwarp();
+            if (lane < nb) A[c][lane] *= ip;
+            __syncwarp();
+            const double pc = lane < nb ? A[c][lane] : 0.0;
+            for (int i = 0; i < nb; ++i) {
+                if (i == c) continue;
+                const double f = A[i][c];
+                __syncwarp();
+                if (f == 0.0) continue;
+                if (lane == c) A[i][c] = 0.0;
+                __syncwarp();
+                if (lane < nb) A[i][lane] -= f * pc;
+                __syncwarp();
+            }
+        }
+    }
+    double *out = blk + blk_off[m];
+    if (!coupled || !ok) {
+        for (int i = 0; i < nb; ++i)
+            if (lane < nb) {
+                const double k = row_k[r0 + i / 3];
+                out[i * nb + lane] = (i == lane) ? (k > 0.0 ? 1.0 / k : 1.0) : 0.0;
+            }
+    } else {
+        for (int i = 0; i < nb; ++i) if (lane < nb) out[i * nb + lane] = A[i][lane];
     }
 }
 
@@ -703,7 +778,7 @@ static int ws_ensure(upol_system *s, int m, MinWs **out) {
             // (possibly non-blocking) stream read the tables
             ok = ok && cudaDeviceSynchronize() == cudaSuccess;
         }
-        (void)max_rows;
+        w->max_rows = max_rows;
     }
     if (!ok) { set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__); ws_free(w); return UPOL_ERR_ALLOC; }
     s->min_ws = w;
@@ -743,9 +818,16 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
     }
 
     if (s->mol_hi > s->mol_lo)      // preconditioner blocks of this rank's molecules, current geometry
-        build_blocks_kernel<<<(unsigned)((s->mol_hi - s->mol_lo + 63) / 64), 64, 0, st>>>(
-            (int)s->mol_lo, (int)s->mol_hi, w->mol_row0, w->mol_nrow, w->blk_off, s->row_site, s->r, s->row_qs,
-            s->row_k, s->th_ptr, s->th_row, s->th_u, w->blk);
+    {
+        if (w->max_rows <= 10)        // 3 nrow <= 32: one warp per molecule, block in shared memory
+            build_blocks_warp_kernel<<<(unsigned)((s->mol_hi - s->mol_lo + kBlkWarps - 1) / kBlkWarps), 32 * kBlkWarps, 0, st>>>(
+                (int)s->mol_lo, (int)s->mol_hi, w->mol_row0, w->mol_nrow, w->blk_off, s->row_site, s->r, s->row_qs,
+                s->row_k, s->th_ptr, s->th_row, s->th_u, w->blk);
+        else
+            build_blocks_kernel<<<(unsigned)((s->mol_hi - s->mol_lo + 63) / 64), 64, 0, st>>>(
+                (int)s->mol_lo, (int)s->mol_hi, w->mol_row0, w->mol_nrow, w->blk_off, s->row_site, s->r, s->row_qs,
+                s->row_k, s->th_ptr, s->th_row, s->th_u, w->blk);
+    }
     static const double switch_rel = getenv("UPOL_MIXED_SWITCH") ? atof(getenv("UPOL_MIXED_SWITCH")) : 1e-4;
     init_state_kernel<<<1, 1, 0, st>>>(w->ic, w->sc, o->tol, mixed ? kGatePhaseMixed : kGatePhase64, o->maxiter, switch_rel);
     UPOL_CUDA(cudaMemsetAsync(w->S, 0, sizeof(double) * (size_t)std::max(m, 1) * std::max<int64_t>(n, 1), st));
