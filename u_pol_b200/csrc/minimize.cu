@@ -25,6 +25,7 @@
 // Polak-Ribiere-type preconditioned conjugate gradient under exact line searches.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -938,6 +939,7 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
         launches_per_chunk = w->glaunches;
     }
 
+    static const bool trace = getenv("UPOL_MIN_TRACE") != nullptr;
     // Enqueue chunks of slots, polling the done flag one chunk behind.
     const int max_slots = o->maxiter * 3 + kMaxLineSearch + 8;
     int enq = 0, buf = 0;
@@ -952,6 +954,13 @@ int minimize_compact(upol_system *s, double *x, const upol_min_options *o, upol_
             for (int c = 0; c < check_every && enq < max_slots; ++c, ++enq) { rc = enqueue_slot(); if (rc) return rc; }
         }
         UPOL_CUDA(cudaMemcpyAsync(w->h_ic + buf * I_SIZE, w->ic, sizeof(int) * I_SIZE, cudaMemcpyDeviceToHost, st));
+        if (trace) {     // debug aid (UPOL_MIN_TRACE=1, use check_every = 1): the controller's state after every chunk
+            UPOL_CUDA(cudaMemcpyAsync(w->h_sc, w->sc, sizeof(double) * D_SIZE, cudaMemcpyDeviceToHost, st));
+            UPOL_CUDA(cudaStreamSynchronize(st));
+            const int *ic = w->h_ic + buf * I_SIZE;
+            fprintf(stderr, "[upol minimise] slots %d iter %d evals %d ls %d accept %d gate %d alpha %.4g gnorm %.6e gamma %.4g\n", enq,
+                    ic[I_ITER], ic[I_NEVAL], ic[I_LS], ic[I_ACCEPT], ic[I_GATE], w->h_sc[D_ALPHA_PREV], w->h_sc[D_GNORM], w->h_sc[D_GAMMA]);
+        }
         UPOL_CUDA(cudaEventRecord(w->ev[buf], st));
         pending[buf] = true;
         const int prev = buf ^ 1;
