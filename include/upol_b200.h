@@ -40,8 +40,8 @@ typedef struct upol_system upol_system;   /* one geometry + parameters resident 
 #define UPOL_MIXED 1   /* fp32 pair math in difference form, fp64 accumulation (energy and field) */
 
 /* minimiser methods */
-#define UPOL_LBFGS 0   /* limited-memory BFGS, H0 = diag(1/k), derivative-driven line search  */
-#define UPOL_CG    1   /* diag(1/k)-preconditioned Polak-Ribiere+ conjugate gradient           */
+#define UPOL_LBFGS 0   /* limited-memory BFGS, H0 = gamma * inverse molecule-block Hessian, derivative-driven line search */
+#define UPOL_CG    1   /* the same with history 1: block-preconditioned memoryless BFGS (= PR-type conjugate gradient) */
 
 /* error codes (<0) and numerical flags (>0) */
 #define UPOL_OK               0
@@ -174,8 +174,8 @@ typedef struct upol_min_options {
     double tol;          /* stop when ||grad||_2 <= tol       (polarization.py:178: 1e-4)      */
     int32_t maxiter;     /* jaxopt default 500                                                   */
     int32_t method;      /* UPOL_LBFGS | UPOL_CG                                                 */
-    int32_t precision;   /* UPOL_FP64 | UPOL_MIXED (mixed: fp32 pair math while far from the
-                            minimum, final iterations and the returned energy in fp64)           */
+    int32_t precision;   /* UPOL_FP64 | UPOL_MIXED (mixed: fp32 field until ||g|| <= 1e-4 ||g(d=0)||,
+                            final iterations and the returned energy in fp64)                    */
     int32_t history;     /* L-BFGS memory (default 8)                                            */
     int32_t check_every; /* host polls the device-side convergence flag every this many
                             iterations (default 4); no other host round-trip happens            */

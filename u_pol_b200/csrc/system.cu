@@ -1,6 +1,7 @@
 // System object: HBM-resident geometry/topology, and the evaluation pipeline
-//   prepare (K4a: shells s = r - d, shell columns) -> pair kernel (K1) -> finalize
-//   (K4b/K2: scale, spring, Thole intra, per-block energy partials) -> reduce.
+//   prepare (K4a: shells s = r - d, shell columns) -> pair kernel (K1, static potential fused) -> finalize
+//   (K4b/K2: fold the column splits, scale, spring, Thole intra; the last block sums the energy vector and, in
+//   sharded runs, stores the gradient rows and energy partials into the peers).
 // Replaces the array construction of U_pol/util.py:45-279 (compact O(N) form) and the body of
 // Uind (polarization.py:111-151) + its gradient.
 #include <algorithm>
