@@ -58,21 +58,6 @@ __device__ __forceinline__ double q_over_r3_f64(double q, double x) {
     return ((q * y) * y2) * c;
 }
 
-__device__ __forceinline__ double rsqrt_f64(double x) {
-    // MUFU.RSQ64H seed (rel. error <= 2^-22) + one third-order (Halley) step:
-    // 1/sqrt(x) = y (1-e)^(-1/2),  e = 1 - x y^2  ->  y (1 + e (1/2 + 3e/8)), error O(e^3) ~ 1e-20.
-    // Written as y * fma(e, p, 1) rather than fma(y e, p, y): same five DP instructions, but none of them
-    // reads three distinct registers (a DFMA with three 64-bit register operands takes 3.1 cycles per warp
-    // instead of 2.2 - register-operand bandwidth, profiles/r02_ubench2.txt).
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double t = y * y;
-    const double e = fma(-x, t, 1.0);
-    const double p = fma(0.375, e, 0.5);
-    const double c = fma(e, p, 1.0);
-    return y * c;
-}
-
 // SPLITF (core-force pass): the fields of section A and section B are kept apart, because they are
 // multiplied by different charges of the row afterwards (output comps 0-2 and 3-5, no potential).
 //

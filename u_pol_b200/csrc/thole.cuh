@@ -42,4 +42,19 @@ __device__ inline void thole_hessian(double x, double y, double z, double u, dou
         for (int j = 0; j < 3; ++j) G[i][j] = (i == j ? c : 0.0) + cpr * v[i] * v[j];
 }
 
+// 1/sqrt(x) in fp64: MUFU.RSQ64H seed (rel. error <= 2^-22) + one third-order (Halley) step:
+// 1/sqrt(x) = y (1-e)^(-1/2),  e = 1 - x y^2  ->  y (1 + e (1/2 + 3e/8)), error O(e^3) ~ 1e-20.
+// Written as y * fma(e, p, 1) rather than fma(y e, p, y): same five DP instructions, but none of them
+// reads three distinct registers (a DFMA with three 64-bit register operands takes 3.1 cycles per warp
+// instead of 2.2 - register-operand bandwidth, profiles/r02_ubench2.txt).
+__device__ __forceinline__ double rsqrt_f64(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = y * y;
+    const double e = fma(-x, t, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double c = fma(e, p, 1.0);
+    return y * c;
+}
+
 }  // namespace upol
