@@ -113,6 +113,8 @@ __device__ __forceinline__ double erfcx_0_to_6(double x) {
 template <bool STATIC>
 __global__ void __launch_bounds__(kBlock) ewald_real_kernel(const PairArgs a, const EwaldArgs w) {
     __shared__ double4 sh[kTileCols];
+    __shared__ unsigned char list[kTileCols][kBlock];     // in-range columns of each thread's row (16 KB)
+    static_assert(kTileCols <= 256, "column indices are stored as bytes");
     if (a.gate != nullptr && (*a.gate & kGateDone) != 0) return;
     const double4 *__restrict__ cols = static_cast<const double4 *>(a.cols);
     const int tid = threadIdx.x;
@@ -132,24 +134,35 @@ __global__ void __launch_bounds__(kBlock) ewald_real_kernel(const PairArgs a, co
         __syncthreads();
         const bool isB = t >= a.n_tiles_a;
         const int lo = (isB ? loB : loA) - base, len = isB ? lenB : lenA;
-        double pt = 0.0;
-#pragma unroll 2
+        // Two phases per tile.  Only ~40 % of the pairs lie inside the screening range, but in a fused loop
+        // nearly every warp iteration has SOME lane in range, so every pair pays for the special functions.
+        // Phase 1 only measures distances and lets each thread note the in-range columns of its row (one byte each,
+        // list[slot][thread]: conflict-free); phase 2 runs the expensive part over the thread's own list, so a warp
+        // iterates max-over-lanes(count) ~ 50 % of the tile instead of 100 %.  Same columns in the same order per
+        // row: identical sums.
+        int cnt = 0;
+#pragma unroll 4
         for (int j = 0; j < kTileCols; ++j) {
             const double4 c = sh[j];
             const double dx = wrap(c.x - sx, w.Lx, w.iLx), dy = wrap(c.y - sy, w.Ly, w.iLy), dz = wrap(c.z - sz, w.Lz, w.iLz);
             const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
             const bool ok = !((unsigned)(j - lo) < (unsigned)len) && r2 > kZeroR2 && r2 < w.cut2 && c.w != 0.0;
-            if (ok) {
-                // 1/r from the MUFU seed + one third-order step (as the open-boundary kernels), erfc(x) = exp(-x^2) erfcx(x)
-                const double inv = rsqrt_f64(r2), x = w.kappa * (r2 * inv);
-                const double ex = exp(-(w.kappa * w.kappa) * r2);
-                const double ec = ex * erfcx_0_to_6(x);
-                const double pot = c.w * ec * inv;
-                pt += pot;
-                if (!STATIC) {
-                    const double wq = (pot + c.w * w.c2 * ex) * (inv * inv);
-                    fx = fma(wq, dx, fx); fy = fma(wq, dy, fy); fz = fma(wq, dz, fz);
-                }
+            if (ok) { list[cnt][tid] = (unsigned char)j; ++cnt; }
+        }
+        double pt = 0.0;
+        for (int q = 0; q < cnt; ++q) {
+            const double4 c = sh[list[q][tid]];
+            const double dx = wrap(c.x - sx, w.Lx, w.iLx), dy = wrap(c.y - sy, w.Ly, w.iLy), dz = wrap(c.z - sz, w.Lz, w.iLz);
+            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            // 1/r from the MUFU seed + one third-order step (as the open-boundary kernels), erfc(x) = exp(-x^2) erfcx(x)
+            const double inv = rsqrt_f64(r2), x = w.kappa * (r2 * inv);
+            const double ex = exp(-(w.kappa * w.kappa) * r2);
+            const double ec = ex * erfcx_0_to_6(x);
+            const double pot = c.w * ec * inv;
+            pt += pot;
+            if (!STATIC) {
+                const double wq = (pot + c.w * w.c2 * ex) * (inv * inv);
+                fx = fma(wq, dx, fx); fy = fma(wq, dy, fy); fz = fma(wq, dz, fz);
             }
         }
         if (isB) phB += pt; else phA += pt;
