@@ -193,9 +193,10 @@ def test_plain_c_program_through_the_c_abi(tmp_path):
 
 
 def test_one_pair_kernel_launch_per_evaluation():
-    """An evaluation is prepare -> ONE pair kernel -> finalize (its last block sums the energy vector) -> scatter:
-    the fp64 pass forms the static potential in the same launch (no separate static pass), and a mixed call
-    launches the difference-form kernel only (no fp64 pair kernel, no static pass)."""
+    """An evaluation is prepare -> ONE pair kernel -> finalize (its last block sums the energy vector, and it writes
+    the (nsite,3) gradient itself): three launches.  The fp64 pass forms the static potential in the same launch (no
+    separate static pass), and a mixed call launches the difference-form kernel only (no fp64 pair kernel, no static
+    pass).  A row shard keeps the separate zero-filling scatter (four launches)."""
     s = synth.imidazole_box(20, seed=91)
     D = synth.random_displacements(s, seed=92)
     sys_ = UindSystem.from_drude_system(s)
@@ -203,15 +204,24 @@ def test_one_pair_kernel_launch_per_evaluation():
     n0 = sys_.launch_count()
     e64, g64 = sys_.energy_grad(d_dev)                       # static not cached yet: fused into the pass
     n1 = sys_.launch_count()
-    assert n1 - n0 == 4
+    assert n1 - n0 == 3
     em, gm = sys_.energy_grad(d_dev, precision="mixed")
-    assert sys_.launch_count() - n1 == 4
+    assert sys_.launch_count() - n1 == 3
     assert abs(float(em[0]) - float(e64[0])) <= 1e-5 * abs(float(e64[0]))
     assert float((gm - g64).abs().max()) <= 1e-5 * float(g64.abs().max())
     # the static potential was kept by the fused pass: the second fp64 evaluation gives the same bits
     e2, g2 = sys_.energy_grad(d_dev)
     assert torch.equal(g2, g64) and abs(float(e2[0]) - float(e64[0])) <= 1e-13 * abs(float(e64[0]))
     assert float(e2[5]) == float(e64[5]) != 0.0              # E_STATIC reported either way
+    # non-polarisable sites: exact zeros written by the finalize kernel; a shard zero-fills the other rows' sites too
+    nonpol = torch.as_tensor((s.q_shell.reshape(-1) == 0)).cuda()
+    assert bool((g64[nonpol] == 0).all()) and bool((g64[~nonpol].abs().sum(dim=1) > 0).all())
+    sys_.set_row_range(3, 11)
+    n2 = sys_.launch_count()
+    _, gs = sys_.energy_grad(d_dev)
+    assert sys_.launch_count() - n2 == 4
+    na = s.natoms
+    assert torch.equal(gs[3 * na:11 * na], g64[3 * na:11 * na]) and bool((gs[:3 * na] == 0).all()) and bool((gs[11 * na:] == 0).all())
 
 
 def test_dense_wrappers_reuse_the_device_system():

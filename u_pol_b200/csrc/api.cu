@@ -356,9 +356,12 @@ int upol_uind_energy_grad_dev(upol_system *s, const double *d, int precision, do
     const bool px = s->p2p && s->nranks > 1;
     double *gbuf = s->gc;
     if (px) { o.gx = make_eval_xchg(s, grad != nullptr); gbuf = s->xg + o.gx.g_off; }
+    // one rank evaluating all its rows: the finalize kernel writes the (nsite,3) layout itself, no scatter launch
+    const bool direct = grad != nullptr && s->nranks == 1 && s->row_lo == 0 && s->row_hi == s->nd && s->nd > 0;
+    if (direct) o.g_full = grad;
     int rc = sys_eval_compact(s, s->dc, o, energy, gbuf, st);
     if (rc) return rc;
-    if (grad) {
+    if (grad && !direct) {
         if (s->nranks > 1 && !px) { rc = comm_allgather_rows(s, gbuf, st); if (rc) return rc; }
         rc = sys_scatter_g(s, gbuf, grad, st);
     }

@@ -221,6 +221,7 @@ struct EvalOpts {
     const int *gate = nullptr;     // minimiser gate word (see kGate*)
     bool phase_switch = false;     // minimiser: launch both field kernels, gate picks one
     const double *d_full = nullptr; // displacements in the (nsite,3) layout: gathered into s->dc by the prepare kernel
+    double *g_full = nullptr;       // gradient also in the (nsite,3) layout, written by the finalize kernel (single rank, all rows)
     bool shells_ready = false;      // shell rows / columns already match d (minimiser: written by its update kernel)
     EvalXchg gx = {0, 0, 1, 0, 0, nullptr, nullptr, nullptr, 0, 0};   // peer-memory exchange instead of NCCL (reduce_ranks)
 };

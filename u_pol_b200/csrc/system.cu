@@ -189,7 +189,7 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
                      const double *__restrict__ th_u, double *__restrict__ phi_static,
                      bool with_grad, double *__restrict__ gc, double *__restrict__ eblock,
                      int *__restrict__ ticket, double *__restrict__ e_out, double *__restrict__ e_static, int e_flags,
-                     const EvalXchg xg) {
+                     const EvalXchg xg, double *__restrict__ g_full, int nd_total, int nsite) {
     __shared__ double sm[kFinBlock / 32];
     __shared__ int is_last;
     __shared__ double fold[kFinBlock / FR][FR][kPartComps];
@@ -245,6 +245,16 @@ finalize_rows_kernel(int n_rows, int row0, int n_split_pot, int n_split_f64, int
         if (with_grad) {
             gc[3 * i] = gx; gc[3 * i + 1] = gy; gc[3 * i + 2] = gz;
             g2 = gx * gx + gy * gy + gz * gz;
+            if (g_full != nullptr) {
+                // the reference's (nsite,3) layout written here as well (no separate scatter launch): the row's own
+                // site, and exact zeros on the non-polarisable sites up to the next Drude site (and before the first)
+                const int s_next = (i + 1 < nd_total) ? row_site[i + 1] : nsite;
+                g_full[3 * sa] = gx; g_full[3 * sa + 1] = gy; g_full[3 * sa + 2] = gz;
+                for (int q = (i == 0 ? 0 : sa + 1); q < s_next; ++q) {
+                    if (q == sa) continue;
+                    g_full[3 * q] = 0.0; g_full[3 * q + 1] = 0.0; g_full[3 * q + 2] = 0.0;
+                }
+            }
             if (xg.on && xg.push_grad) {
                 // fused all-gather: the row goes straight into every peer's gradient buffer (NVLink stores)
                 for (int rk = 0; rk < xg.nranks; ++rk) {
@@ -589,7 +599,8 @@ int sys_eval_compact(upol_system *s, const double *dcmp, const EvalOpts &o, doub
                                       s->row_site, s->r, dcmp, s->row_qs, s->row_k,
                                       s->th_ptr, s->th_row, s->th_u,
                                       (o.want_energy && !diff_energy) ? s->phi_static : nullptr, o.want_grad, gcmp,
-                                      s->eblock, s->ticket, e, s->e_static, e_flags, xg);
+                                      s->eblock, s->ticket, e, s->e_static, e_flags, xg,
+                                      o.want_grad ? o.g_full : nullptr, (int)s->nd, (int)s->nsite);
         UPOL_CUDA(cudaGetLastError());
         ++s->launches;
         if (fuse_static) s->static_valid = true;
